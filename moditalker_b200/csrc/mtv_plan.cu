@@ -1,0 +1,751 @@
+// mtv_plan.cu — handle, weight store, launch plan and the C ABI of libmtv_b200.so.
+//
+// The plan is the B200 replacement for UNetModel.forward's Python control flow
+// (MToV/models/ddpm/unet.py:995-1117): the architecture is walked ONCE per batch
+// size into a flat list of kernel launches over pre-allocated HBM buffers; the body
+// of the list is then captured into a CUDA graph, so a denoising step is
+// {copy t, pack inputs, one graph launch, copy eps} instead of ~2300 framework
+// kernels.
+#include "../../include/mtv_b200.h"
+#include "mtv_kernels.cuh"
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+using namespace mtv;
+
+namespace {
+
+thread_local std::string g_err;
+
+struct MtvError : std::runtime_error { using std::runtime_error::runtime_error; };
+#define CK(expr)                                                                               \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess)                                                                     \
+      throw MtvError(std::string(#expr) + " failed: " + cudaGetErrorString(_e) + " (" + __FILE__ + ":" + \
+                     std::to_string(__LINE__) + ")");                                          \
+  } while (0)
+
+// ------------------------------------------------------------------ architecture walk
+// Mirrors moditalker_b200/arch.py (same traversal of unet.py:710-975); the Python
+// test tests/test_arch.py compares the two weight-name lists.
+struct ResDesc { std::string name; int cin = 0, cout = 0; int updown = RS_NONE; int film_off = 0; };
+struct AttnDesc { std::string name; int C = 0; bool joint = false; };
+struct Layer { bool is_res = false; ResDesc r; AttnDesc a; };
+struct StageDesc {
+  std::vector<Layer> layers; bool has_joint = false; AttnDesc joint;
+  int skip_ch = 0, level_in = 0, level_out = 0;
+};
+struct Arch {
+  std::vector<StageDesc> in; StageDesc mid; std::vector<StageDesc> out;
+  int head_ch = 0; int J = 0;
+};
+
+Arch build_arch(const MtvConfig& c) {
+  Arch A;
+  const int mc = c.model_channels;
+  auto res_layer = [&](const std::string& n, int cin, int cout, int ud) {
+    Layer l; l.is_res = true; l.r.name = n; l.r.cin = cin; l.r.cout = cout; l.r.updown = ud;
+    l.r.film_off = A.J; A.J += 2 * cout; return l;
+  };
+  auto attn_layer = [&](const std::string& n, int C, bool joint) {
+    Layer l; l.is_res = false; l.a.name = n; l.a.C = C; l.a.joint = joint; return l;
+  };
+  std::vector<int> skip = {mc};
+  A.in.emplace_back();   // stem
+  int ch = mc, level = 0, idx = 1;
+  for (int li = 0; li < c.num_levels; ++li) {
+    const int mult = c.channel_mult[li];
+    for (int k = 0; k < c.num_res_blocks; ++k) {
+      StageDesc st; st.level_in = st.level_out = level;
+      const std::string p = "input_blocks." + std::to_string(idx);
+      st.layers.push_back(res_layer(p + ".0", ch, mult * mc, RS_NONE));
+      ch = mult * mc;
+      if (c.attn_at_level[li]) st.layers.push_back(attn_layer(p + ".1", ch, false));
+      st.has_joint = true; st.joint = attn_layer("input_attns." + std::to_string(idx), ch, true).a;
+      A.in.push_back(st); skip.push_back(ch); ++idx;
+    }
+    if (li != c.num_levels - 1) {
+      StageDesc st; st.level_in = level; st.level_out = level + 1;
+      st.layers.push_back(res_layer("input_blocks." + std::to_string(idx) + ".0", ch, ch, RS_DOWN2));
+      st.has_joint = true; st.joint = attn_layer("input_attns." + std::to_string(idx), ch, true).a;
+      A.in.push_back(st); skip.push_back(ch); ++idx; ++level;
+    }
+  }
+  A.mid.level_in = A.mid.level_out = level;
+  A.mid.layers.push_back(res_layer("middle_block.0", ch, ch, RS_NONE));
+  A.mid.layers.push_back(attn_layer("middle_block.1", ch, false));
+  A.mid.layers.push_back(res_layer("middle_block.2", ch, ch, RS_NONE));
+  A.mid.has_joint = true; A.mid.joint = attn_layer("mid_attn", ch, true).a;
+  int oidx = 0;
+  for (int li = c.num_levels - 1; li >= 0; --li) {
+    const int mult = c.channel_mult[li];
+    for (int i = 0; i <= c.num_res_blocks; ++i) {
+      const int ich = skip.back(); skip.pop_back();
+      StageDesc st; st.skip_ch = ich; st.level_in = st.level_out = level;
+      const std::string p = "output_blocks." + std::to_string(oidx);
+      st.layers.push_back(res_layer(p + ".0", ch + ich, mc * mult, RS_NONE));
+      ch = mc * mult;
+      int nxt = 1;
+      if (c.attn_at_level[li]) { st.layers.push_back(attn_layer(p + "." + std::to_string(nxt), ch, false)); ++nxt; }
+      if (li && i == c.num_res_blocks) {
+        st.layers.push_back(res_layer(p + "." + std::to_string(nxt), ch, ch, RS_UP2));
+        --level; st.level_out = level;
+      }
+      st.has_joint = true; st.joint = attn_layer("output_attns." + std::to_string(oidx), ch, true).a;
+      A.out.push_back(st); ++oidx;
+    }
+  }
+  A.head_ch = ch;
+  return A;
+}
+
+// ------------------------------------------------------------------ weights
+enum { WK_PLAIN = 0, WK_CONV = 1 };
+struct Weight {
+  std::string name; std::vector<int64_t> shape; size_t elems = 0;
+  float* dev = nullptr; bool owned = true; bool loaded = false; int kind = WK_PLAIN;
+};
+
+struct Tensor { float* p = nullptr; int C = 0; int level = 0; };
+
+struct RunCtx {
+  const float* x = nullptr; const float* cond = nullptr; const float* image_cond = nullptr;
+  int64_t ic_len = 0; const int64_t* t = nullptr; float* out = nullptr;
+};
+
+struct Op {
+  std::string name; int phase = 1;      // 0 = before graph (reads caller pointers), 1 = graph body, 2 = after
+  int launches = 1; double flops = 0, bytes = 0;
+  std::function<cudaError_t(cudaStream_t)> fn;
+};
+
+struct Plan {
+  int B = 0;
+  std::vector<Op> ops;
+  std::vector<void*> allocs; size_t alloc_bytes = 0;
+  std::map<std::string, Tensor> taps;
+  RunCtx ctx;
+  cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr; int runs = 0;
+  ~Plan() {
+    if (exec) cudaGraphExecDestroy(exec);
+    if (graph) cudaGraphDestroy(graph);
+    for (void* p : allocs) cudaFree(p);
+  }
+};
+
+}  // namespace
+
+struct MtvHandle_t {
+  MtvConfig cfg{}; Arch arch; int num_sms = 148;
+  std::vector<Weight> weights; std::unordered_map<std::string, int> windex;
+  std::vector<void*> allocs;
+  float* emb_wall = nullptr; float* emb_ball = nullptr; float* freqs = nullptr;
+  std::unordered_map<std::string, float*> bias_sum;   // ResBlock name -> conv2.bias + skip.bias
+  bool dirty = true; bool use_graph = true;
+  std::map<int, std::unique_ptr<Plan>> plans;
+  Plan* last_plan = nullptr;
+  int64_t weight_bytes = 0;
+
+  float* dalloc(size_t bytes) {
+    void* p = nullptr; CK(cudaMalloc(&p, bytes)); allocs.push_back(p); return (float*)p;
+  }
+  int add_weight(const std::string& name, std::vector<int64_t> shape, int kind, float* view = nullptr) {
+    Weight w; w.name = name; w.shape = shape; w.kind = kind; w.elems = 1;
+    for (auto d : shape) w.elems *= (size_t)d;
+    if (view) { w.dev = view; w.owned = false; } else { w.dev = dalloc(w.elems * sizeof(float)); }
+    weight_bytes += (int64_t)w.elems * 4;
+    windex[name] = (int)weights.size(); weights.push_back(w);
+    return (int)weights.size() - 1;
+  }
+  float* W(const std::string& name) const {
+    auto it = windex.find(name);
+    if (it == windex.end()) throw MtvError("internal: unknown weight " + name);
+    return weights[it->second].dev;
+  }
+};
+
+namespace {
+
+Geo level_geo(const MtvConfig& c, int level) { return make_geo(c.image_size >> level, (c.image_size / 2) >> level); }
+
+void register_weights(MtvHandle_t* h) {
+  const MtvConfig& c = h->cfg; const Arch& A = h->arch;
+  const int mc = c.model_channels, ted = 4 * mc;
+  h->emb_wall = h->dalloc((size_t)A.J * ted * sizeof(float));
+  h->emb_ball = h->dalloc((size_t)A.J * sizeof(float));
+  h->add_weight("time_embed.0.weight", {ted, mc}, WK_PLAIN);
+  h->add_weight("time_embed.0.bias", {ted}, WK_PLAIN);
+  h->add_weight("time_embed.2.weight", {ted, ted}, WK_PLAIN);
+  h->add_weight("time_embed.2.bias", {ted}, WK_PLAIN);
+  h->add_weight("input_blocks.0.0.weight", {mc, 4 * c.in_channels, 3, 3}, WK_CONV);
+  h->add_weight("input_blocks.0.0.bias", {mc}, WK_PLAIN);
+  auto reg_res = [&](const ResDesc& r) {
+    const std::string& p = r.name;
+    h->add_weight(p + ".in_layers.0.weight", {r.cin}, WK_PLAIN);
+    h->add_weight(p + ".in_layers.0.bias", {r.cin}, WK_PLAIN);
+    h->add_weight(p + ".in_layers.2.weight", {r.cout, r.cin, 3, 3}, WK_CONV);
+    h->add_weight(p + ".in_layers.2.bias", {r.cout}, WK_PLAIN);
+    h->add_weight(p + ".emb_layers.1.weight", {2 * r.cout, ted}, WK_PLAIN, h->emb_wall + (size_t)r.film_off * ted);
+    h->add_weight(p + ".emb_layers.1.bias", {2 * r.cout}, WK_PLAIN, h->emb_ball + r.film_off);
+    h->add_weight(p + ".out_layers.0.weight", {r.cout}, WK_PLAIN);
+    h->add_weight(p + ".out_layers.0.bias", {r.cout}, WK_PLAIN);
+    h->add_weight(p + ".out_layers.3.weight", {r.cout, r.cout, 3, 3}, WK_CONV);
+    h->add_weight(p + ".out_layers.3.bias", {r.cout}, WK_PLAIN);
+    if (r.cin != r.cout) {
+      h->add_weight(p + ".skip_connection.weight", {r.cout, r.cin, 1, 1}, WK_CONV);
+      h->add_weight(p + ".skip_connection.bias", {r.cout}, WK_PLAIN);
+      h->bias_sum[p] = h->dalloc((size_t)r.cout * sizeof(float));
+    }
+  };
+  auto reg_attn = [&](const AttnDesc& a) {
+    const std::string& p = a.name;
+    h->add_weight(p + ".norm.weight", {a.C}, WK_PLAIN);
+    h->add_weight(p + ".norm.bias", {a.C}, WK_PLAIN);
+    h->add_weight(p + ".qkv.weight", {3 * a.C, a.C, 1}, WK_CONV);
+    h->add_weight(p + ".qkv.bias", {3 * a.C}, WK_PLAIN);
+    h->add_weight(p + ".proj_out.weight", {a.C, a.C, 1}, WK_CONV);
+    h->add_weight(p + ".proj_out.bias", {a.C}, WK_PLAIN);
+  };
+  auto reg_stage = [&](const StageDesc& st) {
+    for (const Layer& l : st.layers) { if (l.is_res) reg_res(l.r); else reg_attn(l.a); }
+    if (st.has_joint) reg_attn(st.joint);
+  };
+  for (size_t i = 1; i < A.in.size(); ++i) reg_stage(A.in[i]);
+  reg_stage(A.mid);
+  for (const StageDesc& st : A.out) reg_stage(st);
+  h->add_weight("out.0.weight", {A.head_ch}, WK_PLAIN);
+  h->add_weight("out.0.bias", {A.head_ch}, WK_PLAIN);
+  h->add_weight("out.2.weight", {c.out_channels, mc, 3, 3}, WK_CONV);
+  h->add_weight("out.2.bias", {c.out_channels}, WK_PLAIN);
+
+  // timestep_embedding frequencies, fp32 like the reference (diffusionmodules.py:118-121)
+  const int half = mc / 2;
+  std::vector<float> fr(half);
+  const float neg_log = (float)(-std::log(10000.0));
+  for (int i = 0; i < half; ++i) fr[i] = expf(neg_log * (float)i / (float)half);
+  h->freqs = h->dalloc(half * sizeof(float));
+  CK(cudaMemcpy(h->freqs, fr.data(), half * sizeof(float), cudaMemcpyHostToDevice));
+}
+
+void ensure_ready(MtvHandle_t* h, cudaStream_t s) {
+  if (!h->dirty) return;
+  for (const Weight& w : h->weights)
+    if (!w.loaded) throw MtvError("weight not loaded: " + w.name);
+  for (auto& kv : h->bias_sum) {
+    const std::string& p = kv.first;
+    const int n = (int)h->weights[h->windex.at(p + ".out_layers.3.bias")].elems;
+    CK(launch_add_vec(h->W(p + ".out_layers.3.bias"), h->W(p + ".skip_connection.bias"), kv.second, n, s));
+  }
+  h->dirty = false;
+}
+
+// ------------------------------------------------------------------ plan builder
+struct NormRef { float* a = nullptr; float* d = nullptr; int nseg = 0; };
+
+struct Builder {
+  MtvHandle_t* h; Plan* pl; int B;
+  Builder(MtvHandle_t* h_, Plan* p_) : h(h_), pl(p_), B(p_->B) {}
+
+  void* dalloc(size_t bytes, bool zero = false) {
+    void* p = nullptr; CK(cudaMalloc(&p, bytes));
+    if (zero) CK(cudaMemset(p, 0, bytes));
+    pl->allocs.push_back(p); pl->alloc_bytes += bytes; return p;
+  }
+  Geo geo(int level) const { return level_geo(h->cfg, level); }
+  Tensor T(int C, int level) {
+    Tensor t; t.C = C; t.level = level;
+    t.p = (float*)dalloc((size_t)B * geo(level).L * C * sizeof(float)); return t;
+  }
+  void set_segs(int level, bool joint, int& nseg, int* off) const {
+    const Geo g = geo(level);
+    if (joint) { nseg = 1; off[0] = 0; off[1] = g.L; off[2] = off[3] = g.L; }
+    else { nseg = 3; off[0] = 0; off[1] = g.res * g.res; off[2] = off[1] + g.t * g.res; off[3] = g.L; }
+  }
+
+  NormRef gn(const std::string& name, const Tensor& x0, const Tensor* x1, bool joint,
+             const float* gamma, const float* beta, int film_off) {
+    GnParams P{};
+    P.src0 = x0.p; P.C0 = x0.C; P.src1 = x1 ? x1->p : nullptr; P.C1 = x1 ? x1->C : 0;
+    const int C = P.C0 + P.C1;
+    if (C % 32) throw MtvError("GroupNorm32 needs channels % 32 == 0 at " + name);
+    P.B = B; P.L = geo(x0.level).L;
+    set_segs(x0.level, joint, P.nseg, P.seg_off);
+    P.gamma = gamma; P.beta = beta;
+    if (film_off >= 0) { P.film = film_buf + film_off; P.film_stride = h->arch.J; }
+    P.nrm_a = (float*)dalloc((size_t)B * P.nseg * C * sizeof(float));
+    P.nrm_d = (float*)dalloc((size_t)B * P.nseg * C * sizeof(float));
+    P.sums = (double*)dalloc((size_t)B * P.nseg * 64 * sizeof(double), true);
+    P.counter = (unsigned*)dalloc((size_t)B * P.nseg * sizeof(unsigned), true);
+    int maxlen = 0;
+    for (int i = 0; i < P.nseg; ++i) maxlen = std::max(maxlen, P.seg_off[i + 1] - P.seg_off[i]);
+    int chunk = maxlen / 32; chunk = chunk < 4 ? 4 : (chunk > 64 ? 64 : chunk);
+    P.chunk_tokens = chunk;
+    Op op; op.name = "gn_stats:" + name; op.bytes = (double)B * P.L * C * 4;
+    op.fn = [P](cudaStream_t s) { return launch_gn_stats(P, s); };
+    pl->ops.push_back(op);
+    return NormRef{P.nrm_a, P.nrm_d, P.nseg};
+  }
+
+  void conv(const std::string& name, ConvParams P, int phase = 1, bool out_is_ctx = false) {
+    P.B = B;
+    double K = 0;
+    for (int s = 0; s < P.nsegs; ++s) {
+      const int Ct = P.seg[s].C0 + P.seg[s].C1;
+      if (Ct % 16 || P.seg[s].C0 % 16) throw MtvError("tap-GEMM needs channels % 16 == 0 at " + name);
+      K += (double)P.seg[s].taps * Ct;
+    }
+    if (P.Cout % 4) throw MtvError("tap-GEMM needs Cout % 4 == 0 at " + name);
+    const double M = (double)B * P.geo.L;
+    P.ksplit = conv_simt_pick_ksplit(P, h->num_sms);
+    if (P.ksplit > 1) P.partial = (float*)dalloc((size_t)P.ksplit * (size_t)M * P.Cout * sizeof(float));
+    Op op; op.name = "conv:" + name; op.phase = phase; op.launches = P.ksplit > 1 ? 2 : 1;
+    op.flops = 2.0 * M * P.Cout * K;
+    op.bytes = 4.0 * (K * P.Cout + M * K / (P.seg[0].taps) + M * P.Cout);
+    Plan* plan = pl;
+    if (out_is_ctx) op.fn = [P, plan](cudaStream_t s) { ConvParams Q = P; Q.out = plan->ctx.out; return launch_conv_simt(Q, s); };
+    else            op.fn = [P](cudaStream_t s) { return launch_conv_simt(P, s); };
+    pl->ops.push_back(op);
+  }
+
+  float* film_buf = nullptr;
+
+  Tensor res_block(const ResDesc& r, const Tensor& x0, const Tensor* x1, int level_in, int level_out) {
+    const std::string& p = r.name;
+    const int cin = x0.C + (x1 ? x1->C : 0);
+    if (cin != r.cin) throw MtvError("internal: channel mismatch at " + p);
+    NormRef n1 = gn(p + ".in_layers.0", x0, x1, false, h->W(p + ".in_layers.0.weight"), h->W(p + ".in_layers.0.bias"), -1);
+    Tensor hmid = T(r.cout, level_out);
+    {
+      ConvParams P{}; P.nsegs = 1; P.geo = geo(level_out); P.Cout = r.cout;
+      KSeg& S = P.seg[0];
+      S.src0 = x0.p; S.C0 = x0.C; S.src1 = x1 ? x1->p : nullptr; S.C1 = x1 ? x1->C : 0;
+      S.nrm_a = n1.a; S.nrm_d = n1.d; S.nrm_nseg = 3; S.silu = 1; S.resample = r.updown; S.taps = 9;
+      S.w = h->W(p + ".in_layers.2.weight");
+      P.bias = h->W(p + ".in_layers.2.bias"); P.out = hmid.p;
+      conv(p + ".in_layers.2", P);
+    }
+    NormRef n2 = gn(p + ".out_layers.0", hmid, nullptr, false, h->W(p + ".out_layers.0.weight"),
+                    h->W(p + ".out_layers.0.bias"), r.film_off);
+    Tensor out = T(r.cout, level_out);
+    {
+      ConvParams P{}; P.nsegs = 1; P.geo = geo(level_out); P.Cout = r.cout;
+      KSeg& S = P.seg[0];
+      S.src0 = hmid.p; S.C0 = r.cout; S.nrm_a = n2.a; S.nrm_d = n2.d; S.nrm_nseg = 3; S.silu = 1;
+      S.resample = RS_NONE; S.taps = 9; S.w = h->W(p + ".out_layers.3.weight");
+      if (r.cin != r.cout) {   // 1x1 skip conv folded in as a second K-segment (unet.py:167, 207)
+        P.nsegs = 2; KSeg& K1 = P.seg[1];
+        K1.src0 = x0.p; K1.C0 = x0.C; K1.src1 = x1 ? x1->p : nullptr; K1.C1 = x1 ? x1->C : 0;
+        K1.resample = r.updown; K1.taps = 1; K1.w = h->W(p + ".skip_connection.weight");
+        P.bias = h->bias_sum.at(p);
+      } else {
+        if (x1) throw MtvError("identity skip over a concatenated input is not on the MToV path: " + p);
+        P.bias = h->W(p + ".out_layers.3.bias");
+        P.resid = x0.p; P.resid_mode = r.updown;
+      }
+      P.out = out.p;
+      conv(p + ".out_layers.3", P);
+    }
+    return out;
+  }
+
+  Tensor attn_block(const AttnDesc& a, const Tensor& x, int level) {
+    const std::string& p = a.name;
+    const int C = a.C, heads = h->cfg.num_heads;
+    if (x.C != C) throw MtvError("internal: channel mismatch at " + p);
+    NormRef n = gn(p + ".norm", x, nullptr, a.joint, h->W(p + ".norm.weight"), h->W(p + ".norm.bias"), -1);
+    Tensor qkv = T(3 * C, level);
+    {
+      ConvParams P{}; P.nsegs = 1; P.geo = geo(level); P.Cout = 3 * C;
+      KSeg& S = P.seg[0];
+      S.src0 = x.p; S.C0 = C; S.nrm_a = n.a; S.nrm_d = n.d; S.nrm_nseg = n.nseg; S.silu = 0; S.taps = 1;
+      S.w = h->W(p + ".qkv.weight"); P.bias = h->W(p + ".qkv.bias"); P.out = qkv.p;
+      conv(p + ".qkv", P);
+    }
+    Tensor att = T(C, level);
+    {
+      AttnParams P{}; P.qkv = qkv.p; P.out = att.p; P.B = B; P.L = geo(level).L; P.C = C; P.heads = heads;
+      set_segs(level, a.joint, P.nseg, P.seg_off);
+      const int D = C / heads;
+      if (C % heads || !(D == 16 || D == 32 || D == 64 || D == 128))
+        throw MtvError("attention head dim must be 16/32/64/128 at " + p);
+      Op op; op.name = "attn:" + p;
+      double pairs = 0;
+      for (int i = 0; i < P.nseg; ++i) { const double l = P.seg_off[i + 1] - P.seg_off[i]; pairs += l * l; }
+      op.flops = 4.0 * B * heads * pairs * D;
+      op.bytes = 4.0 * B * P.L * 4 * C;
+      op.fn = [P](cudaStream_t s) { return launch_attn_simt(P, s); };
+      pl->ops.push_back(op);
+    }
+    Tensor out = T(C, level);
+    {
+      ConvParams P{}; P.nsegs = 1; P.geo = geo(level); P.Cout = C;
+      KSeg& S = P.seg[0];
+      S.src0 = att.p; S.C0 = C; S.taps = 1; S.w = h->W(p + ".proj_out.weight");
+      P.bias = h->W(p + ".proj_out.bias"); P.resid = x.p; P.resid_mode = RS_NONE; P.out = out.p;
+      conv(p + ".proj_out", P);
+    }
+    return out;
+  }
+
+  Tensor run_stage(const StageDesc& st, Tensor cur, const Tensor* skip) {
+    int level = st.level_in;
+    bool first = true;
+    for (const Layer& l : st.layers) {
+      if (l.is_res) {
+        const int lo = (l.r.updown == RS_NONE) ? level : (l.r.updown == RS_DOWN2 ? level + 1 : level - 1);
+        cur = res_block(l.r, cur, (first && skip) ? skip : nullptr, level, lo);
+        level = lo;
+      } else {
+        cur = attn_block(l.a, cur, level);
+      }
+      first = false;
+    }
+    if (st.has_joint) cur = attn_block(st.joint, cur, level);
+    return cur;
+  }
+
+  void build() {
+    const MtvConfig& c = h->cfg; const Arch& A = h->arch;
+    const int mc = c.model_channels, ted = 4 * mc;
+    Plan* plan = pl;
+    // ---- caller inputs -> internal buffers (outside the graph)
+    int64_t* t_buf = (int64_t*)dalloc((size_t)B * sizeof(int64_t));
+    {
+      Op op; op.name = "copy_t"; op.phase = 0; op.launches = 0;
+      const int Bc = B;
+      op.fn = [plan, t_buf, Bc](cudaStream_t s) {
+        return cudaMemcpyAsync(t_buf, plan->ctx.t, (size_t)Bc * sizeof(int64_t), cudaMemcpyDeviceToDevice, s);
+      };
+      pl->ops.push_back(op);
+    }
+    Tensor xin = T(4 * c.in_channels, 0);
+    {
+      PackParams P{}; P.B = B; P.cx = c.in_channels; P.cc = 2 * c.in_channels; P.ci = c.in_channels; P.out = xin.p;
+      Op op; op.name = "pack_in"; op.phase = 0;
+      op.fn = [plan, P](cudaStream_t s) {
+        PackParams Q = P; Q.x = plan->ctx.x; Q.cond = plan->ctx.cond; Q.image_cond = plan->ctx.image_cond;
+        Q.ic_len = plan->ctx.ic_len; return launch_pack_in(Q, s);
+      };
+      pl->ops.push_back(op);
+    }
+    // ---- timestep embedding + every ResBlock's FiLM scale/shift
+    film_buf = (float*)dalloc((size_t)B * A.J * sizeof(float));
+    {
+      EmbParams P{}; P.t = t_buf; P.B = B; P.mc = mc; P.ted = ted; P.freqs = h->freqs;
+      P.w1 = h->W("time_embed.0.weight"); P.b1 = h->W("time_embed.0.bias");
+      P.w2 = h->W("time_embed.2.weight"); P.b2 = h->W("time_embed.2.bias");
+      P.wall = h->emb_wall; P.ball = h->emb_ball; P.J = A.J;
+      P.temb = (float*)dalloc((size_t)B * mc * sizeof(float));
+      P.h1 = (float*)dalloc((size_t)B * ted * sizeof(float));
+      P.semb = (float*)dalloc((size_t)B * ted * sizeof(float));
+      P.film = film_buf;
+      Op op; op.name = "emb"; op.launches = 4;
+      op.flops = 2.0 * B * ((double)ted * mc + (double)ted * ted + (double)A.J * ted);
+      op.bytes = 4.0 * ((double)ted * mc + (double)ted * ted + (double)A.J * ted);
+      op.fn = [P](cudaStream_t s) { return launch_emb(P, s); };
+      pl->ops.push_back(op);
+    }
+    // ---- encoder
+    std::vector<Tensor> skips;
+    Tensor cur;
+    {
+      cur = T(mc, 0);
+      ConvParams P{}; P.nsegs = 1; P.geo = geo(0); P.Cout = mc;
+      KSeg& S = P.seg[0]; S.src0 = xin.p; S.C0 = xin.C; S.taps = 9; S.w = h->W("input_blocks.0.0.weight");
+      P.bias = h->W("input_blocks.0.0.bias"); P.out = cur.p;
+      conv("input_blocks.0.0", P);
+      pl->taps["in0"] = cur; skips.push_back(cur);
+    }
+    for (size_t i = 1; i < A.in.size(); ++i) {
+      cur = run_stage(A.in[i], cur, nullptr);
+      cur.level = A.in[i].level_out;
+      pl->taps["in" + std::to_string(i)] = cur; skips.push_back(cur);
+    }
+    cur = run_stage(A.mid, cur, nullptr);
+    pl->taps["mid"] = cur;
+    for (size_t i = 0; i < A.out.size(); ++i) {
+      Tensor sk = skips.back(); skips.pop_back();
+      if (sk.C != A.out[i].skip_ch) throw MtvError("internal: skip stack mismatch");
+      cur = run_stage(A.out[i], cur, &sk);
+      cur.level = A.out[i].level_out;
+      pl->taps["out" + std::to_string(i)] = cur;
+    }
+    // ---- head: GN -> SiLU -> conv3x3 -> channel-major eps (unet.py:971-975, 1103-1112)
+    NormRef nh = gn("out.0", cur, nullptr, false, h->W("out.0.weight"), h->W("out.0.bias"), -1);
+    float* eps_buf = (float*)dalloc((size_t)B * c.out_channels * geo(0).L * sizeof(float));
+    {
+      ConvParams P{}; P.nsegs = 1; P.geo = geo(0); P.Cout = c.out_channels;
+      KSeg& S = P.seg[0]; S.src0 = cur.p; S.C0 = cur.C; S.nrm_a = nh.a; S.nrm_d = nh.d; S.nrm_nseg = 3; S.silu = 1;
+      S.taps = 9; S.w = h->W("out.2.weight");
+      P.bias = h->W("out.2.bias"); P.out = eps_buf; P.out_chmajor = 1;
+      conv("out.2", P);
+    }
+    {
+      Op op; op.name = "copy_out"; op.phase = 2; op.launches = 0;
+      const size_t bytes = (size_t)B * c.out_channels * geo(0).L * sizeof(float);
+      op.fn = [plan, eps_buf, bytes](cudaStream_t s) {
+        return cudaMemcpyAsync(plan->ctx.out, eps_buf, bytes, cudaMemcpyDeviceToDevice, s);
+      };
+      pl->ops.push_back(op);
+    }
+  }
+};
+
+Plan* get_plan(MtvHandle_t* h, int B) {
+  auto it = h->plans.find(B);
+  if (it != h->plans.end()) return it->second.get();
+  std::unique_ptr<Plan> pl(new Plan());
+  pl->B = B;
+  Builder b(h, pl.get());
+  b.build();
+  CK(cudaDeviceSynchronize());   // memsets of the statistics scratch
+  Plan* raw = pl.get();
+  h->plans[B] = std::move(pl);
+  return raw;
+}
+
+void run_ops(Plan* pl, int phase, cudaStream_t s) {
+  for (Op& op : pl->ops)
+    if (op.phase == phase) {
+      cudaError_t e = op.fn(s);
+      if (e != cudaSuccess) throw MtvError("launch failed at " + op.name + ": " + cudaGetErrorString(e));
+    }
+}
+
+void forward(MtvHandle_t* h, const RunCtx& ctx, int B, cudaStream_t s) {
+  CK(cudaSetDevice(h->cfg.device));
+  ensure_ready(h, s);
+  Plan* pl = get_plan(h, B);
+  pl->ctx = ctx;
+  run_ops(pl, 0, s);
+  if (!h->use_graph) {
+    run_ops(pl, 1, s);
+  } else {
+    if (!pl->exec) {
+      if (pl->runs == 0) {
+        run_ops(pl, 1, s);     // first call runs eagerly (function attributes, lazy module load)
+      } else {
+        CK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+        try { run_ops(pl, 1, s); } catch (...) { cudaGraph_t g; cudaStreamEndCapture(s, &g); throw; }
+        CK(cudaStreamEndCapture(s, &pl->graph));
+        CK(cudaGraphInstantiate(&pl->exec, pl->graph, 0));
+        CK(cudaGraphLaunch(pl->exec, s));
+      }
+    } else {
+      CK(cudaGraphLaunch(pl->exec, s));
+    }
+  }
+  run_ops(pl, 2, s);
+  pl->runs++;
+  h->last_plan = pl;
+}
+
+template <typename F>
+int guarded(F&& f) {
+  try { f(); return 0; }
+  catch (const std::exception& e) { g_err = e.what(); return 1; }
+  catch (...) { g_err = "unknown error"; return 1; }
+}
+
+std::string strip_prefix(const char* name) {
+  std::string n(name);
+  const std::string pre = "diffusion_model.";
+  if (n.compare(0, pre.size(), pre) == 0) n = n.substr(pre.size());
+  return n;
+}
+
+}  // namespace
+
+// ====================================================================== C ABI
+extern "C" {
+
+int mtv_abi_version(void) { return MTV_ABI_VERSION; }
+const char* mtv_last_error(void) { return g_err.c_str(); }
+
+int mtv_create(const MtvConfig* cfg, MtvHandle* out) {
+  return guarded([&] {
+    if (!cfg || !out) throw MtvError("null argument");
+    if (cfg->abi_version != MTV_ABI_VERSION) throw MtvError("MtvConfig.abi_version mismatch");
+    if (cfg->num_levels < 1 || cfg->num_levels > MTV_MAX_LEVELS) throw MtvError("num_levels out of range");
+    if (cfg->image_size != 32) throw MtvError("image_size must be 32 (the tri-plane latent is [B,4,2048])");
+    if (cfg->model_channels % 32) throw MtvError("model_channels must be a multiple of 32");
+    if ((cfg->image_size / 2) >> (cfg->num_levels - 1) < 1) throw MtvError("too many levels for a 16-row plane");
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
+    if (cfg->device < 0 || cfg->device >= ndev) throw MtvError("no such CUDA device");
+    CK(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major != 10)
+      throw MtvError(std::string("libmtv_b200 is built for sm_100a only; device is sm_") + std::to_string(prop.major) +
+                     std::to_string(prop.minor));
+    std::unique_ptr<MtvHandle_t> h(new MtvHandle_t());
+    h->cfg = *cfg; h->num_sms = prop.multiProcessorCount;
+    h->arch = build_arch(*cfg);
+    const char* ng = getenv("MTV_NO_GRAPH");
+    h->use_graph = !(ng && ng[0] == '1');
+    register_weights(h.get());
+    *out = h.release();
+  });
+}
+
+int mtv_destroy(MtvHandle h) {
+  return guarded([&] {
+    if (!h) return;
+    cudaSetDevice(h->cfg.device);
+    cudaDeviceSynchronize();
+    h->plans.clear();
+    for (void* p : h->allocs) cudaFree(p);
+    delete h;
+  });
+}
+
+int mtv_load_weight(MtvHandle h, const char* name, const float* data, const int64_t* shape, int32_t ndim,
+                    int32_t* used, void* stream) {
+  return guarded([&] {
+    if (!h || !name || !data) throw MtvError("null argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    CK(cudaSetDevice(h->cfg.device));
+    const std::string n = strip_prefix(name);
+    auto it = h->windex.find(n);
+    if (it == h->windex.end()) {
+      const bool dead = n.compare(0, 10, "output_bg_") == 0 || n == "zeros";
+      if (!dead) throw MtvError("unexpected key in state dict: " + n);
+      if (used) *used = 0;
+      return;
+    }
+    Weight& w = h->weights[it->second];
+    if ((int)w.shape.size() != ndim) throw MtvError("rank mismatch for " + n);
+    for (int i = 0; i < ndim; ++i)
+      if (w.shape[i] != shape[i]) throw MtvError("size mismatch for " + n);
+    if (w.kind == WK_CONV) {
+      const int Cout = (int)w.shape[0], Cin = (int)w.shape[1];
+      const int taps = (int)(w.elems / ((size_t)Cout * Cin));
+      CK(launch_repack_conv(data, w.dev, Cout, Cin, taps, s));
+    } else {
+      CK(cudaMemcpyAsync(w.dev, data, w.elems * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    }
+    w.loaded = true; h->dirty = true;
+    if (used) *used = 1;
+  });
+}
+
+int mtv_weights_ready(MtvHandle h, int32_t* needed, int32_t* missing) {
+  return guarded([&] {
+    if (!h) throw MtvError("null handle");
+    int miss = 0; std::string first;
+    for (const Weight& w : h->weights)
+      if (!w.loaded) { if (!miss) first = w.name; ++miss; }
+    if (needed) *needed = (int)h->weights.size();
+    if (missing) *missing = miss;
+    if (miss) throw MtvError("missing key in state dict: " + first);
+  });
+}
+
+int mtv_num_weight_names(MtvHandle h) { return h ? (int)h->weights.size() : 0; }
+const char* mtv_weight_name(MtvHandle h, int32_t i) {
+  if (!h || i < 0 || i >= (int)h->weights.size()) return nullptr;
+  return h->weights[i].name.c_str();
+}
+
+int mtv_unet_forward(MtvHandle h, const float* x, const float* cond, const float* image_cond, int64_t image_cond_len,
+                     const int64_t* t, int32_t B, float* out, void* stream) {
+  return guarded([&] {
+    if (!h || !x || !cond || !image_cond || !t || !out) throw MtvError("null argument");
+    if (B < 1) throw MtvError("batch must be >= 1");
+    if (image_cond_len < 1024) throw MtvError("image_cond needs at least the 1024-token xy plane");
+    RunCtx ctx; ctx.x = x; ctx.cond = cond; ctx.image_cond = image_cond; ctx.ic_len = image_cond_len; ctx.t = t; ctx.out = out;
+    forward(h, ctx, B, (cudaStream_t)stream);
+  });
+}
+
+int mtv_ddim_step(MtvHandle h, float* img, const float* eps, const float* noise, int64_t n, float sr, float srm1,
+                  float san, float c, float sigma, int32_t last, void* stream) {
+  return guarded([&] {
+    if (!h || !img || !eps || (!last && !noise)) throw MtvError("null argument");
+    CK(cudaSetDevice(h->cfg.device));
+    CK(launch_ddim_step(img, eps, noise, n, sr, srm1, san, c, sigma, last, (cudaStream_t)stream));
+  });
+}
+
+int mtv_q_sample(MtvHandle h, const float* x_start, const float* noise, int64_t n, float a, float b, float* out,
+                 void* stream) {
+  return guarded([&] {
+    if (!h || !x_start || !noise || !out) throw MtvError("null argument");
+    CK(cudaSetDevice(h->cfg.device));
+    CK(launch_q_sample(x_start, noise, n, a, b, out, (cudaStream_t)stream));
+  });
+}
+
+int mtv_plan_info(MtvHandle h, int32_t B, int64_t* n_launches, int64_t* workspace_bytes, int64_t* weight_bytes) {
+  return guarded([&] {
+    if (!h) throw MtvError("null handle");
+    CK(cudaSetDevice(h->cfg.device));
+    Plan* pl = get_plan(h, B);
+    int64_t n = 0;
+    for (const Op& op : pl->ops) n += op.launches;
+    if (n_launches) *n_launches = n;
+    if (workspace_bytes) *workspace_bytes = (int64_t)pl->alloc_bytes;
+    if (weight_bytes) *weight_bytes = h->weight_bytes;
+  });
+}
+
+int mtv_debug_read(MtvHandle h, const char* tag, float* dst, int64_t dst_elems, void* stream) {
+  return guarded([&] {
+    if (!h || !tag || !dst) throw MtvError("null argument");
+    CK(cudaSetDevice(h->cfg.device));
+    Plan* pl = h->last_plan;
+    if (!pl) throw MtvError("no forward has run yet");
+    auto it = pl->taps.find(tag);
+    if (it == pl->taps.end()) throw MtvError(std::string("unknown tap ") + tag);
+    const Tensor& t = it->second;
+    const Geo g = level_geo(h->cfg, t.level);
+    if ((int64_t)pl->B * g.L * t.C != dst_elems) throw MtvError("tap size mismatch");
+    CK(launch_tok2ch(t.p, dst, pl->B, g.L, t.C, (cudaStream_t)stream));
+  });
+}
+
+int mtv_profile_forward(MtvHandle h, const float* x, const float* cond, const float* image_cond, int64_t image_cond_len,
+                        const int64_t* t, int32_t B, float* out, MtvKernelTime* entries, int32_t cap, int32_t* n,
+                        void* stream) {
+  return guarded([&] {
+    if (!h || !entries || !n) throw MtvError("null argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    CK(cudaSetDevice(h->cfg.device));
+    ensure_ready(h, s);
+    Plan* pl = get_plan(h, B);
+    pl->ctx.x = x; pl->ctx.cond = cond; pl->ctx.image_cond = image_cond; pl->ctx.ic_len = image_cond_len;
+    pl->ctx.t = t; pl->ctx.out = out;
+    cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    int k = 0;
+    for (Op& op : pl->ops) {
+      CK(cudaEventRecord(e0, s));
+      cudaError_t e = op.fn(s);
+      if (e != cudaSuccess) throw MtvError("launch failed at " + op.name + ": " + cudaGetErrorString(e));
+      CK(cudaEventRecord(e1, s));
+      CK(cudaEventSynchronize(e1));
+      float ms = 0; CK(cudaEventElapsedTime(&ms, e0, e1));
+      if (k < cap) {
+        MtvKernelTime& kt = entries[k];
+        snprintf(kt.name, sizeof(kt.name), "%s", op.name.c_str());
+        kt.us = ms * 1000.f; kt.flops = (float)op.flops; kt.bytes = (float)op.bytes;
+      }
+      ++k;
+    }
+    pl->runs++; h->last_plan = pl;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    *n = k < cap ? k : cap;
+  });
+}
+
+}  // extern "C"
