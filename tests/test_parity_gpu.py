@@ -1,0 +1,257 @@
+"""Parity tests proper: the CUDA path (through the C ABI) against
+  (1) fixtures produced by the reference's own modules (tests/golden, written by
+      oracle/make_golden.py), and
+  (2) the CPU oracle on fresh seeded inputs, stage by stage,
+plus size-independent properties at the full configuration (batch independence,
+determinism across eager / captured-graph execution, clamp range of the sampler).
+
+Tolerance (BASELINE.json north_star): rel-L2 <= 1e-3 and max-abs/max-ref <= 1e-3
+against the fp32 reference; the elementwise sampler kernels are bit-exact.
+"""
+import copy
+import ctypes
+
+import pytest
+import torch
+
+from conftest import assert_close, config_by_name, load_golden, max_abs_rel, rel_l2
+from moditalker_b200 import DDPM, BASE_UNET_CONFIG, TINY_UNET_CONFIG, DiffusionWrapper, UNetModel, _lib, build_arch
+from moditalker_b200.arch import param_shapes, tokens_at
+from moditalker_b200.synth import synth_inputs, synth_state_dict
+from oracle.make_golden import TAP_CSTRIDE, TAP_LSTRIDE
+from oracle.unet_oracle import Oracle, ddim_update, schedule
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+_MODELS = {}
+
+
+def model_for(cfg_name, wseed=0):
+    key = (cfg_name, wseed)
+    if key not in _MODELS:
+        cfg = config_by_name(cfg_name)
+        m = DiffusionWrapper(UNetModel(**cfg))
+        m.load_state_dict(synth_state_dict(cfg, wseed, "diffusion_model."), strict=True)
+        _MODELS[key] = m.to(DEV).eval()
+    return _MODELS[key]
+
+
+def run(model, x, cond, ic, t):
+    with torch.no_grad():
+        out = model(x.to(DEV), cond.to(DEV), ic.to(DEV), t.to(DEV))
+    torch.cuda.synchronize()
+    return out.cpu()
+
+
+def stage_levels(cfg):
+    """tap name -> (channels, tokens) from the architecture walk."""
+    arch = build_arch(**cfg)
+    out = {"in0": (arch.model_channels, tokens_at(0))}
+    for i, st in enumerate(arch.input_stages[1:], start=1):
+        out[f"in{i}"] = (st.joint.channels, tokens_at(st.level_out))
+    out["mid"] = (arch.middle.joint.channels, tokens_at(arch.middle.level_out))
+    for i, st in enumerate(arch.output_stages):
+        out[f"out{i}"] = (st.joint.channels, tokens_at(st.level_out))
+    return out
+
+
+def test_native_plan_reads_exactly_the_live_weights():
+    for name in ("tiny", "base"):
+        cfg = config_by_name(name)
+        um = model_for(name).diffusion_model
+        lib, h = um.native_handle()
+        native = sorted(lib.mtv_weight_name(h, i).decode() for i in range(lib.mtv_num_weight_names(h)))
+        live = sorted(n for n, _ in param_shapes(build_arch(**cfg), include_dead=False) if n != "zeros")
+        assert native == live
+
+
+@pytest.mark.parametrize("name", ["unet_tiny_b2", "unet_base_b1", "unet_base_b2", "unet_longvid_b1"])
+def test_forward_matches_reference_fixture(name):
+    g = load_golden(name)
+    cfg = config_by_name(g["config"])
+    model = model_for(str(g["config"]), int(g["wseed"]))
+    B = int(g["B"])
+    x, cond, ic, t = synth_inputs(B, int(g["iseed"]), int(g["ic_len"]), [int(v) for v in g["t"]])
+    eps = run(model, x, cond, ic, t)
+    report = []
+    lv = stage_levels(cfg)
+    for k in sorted(k for k in g if k.startswith("tap_")):
+        C, L = lv[k[4:]]
+        got = model.diffusion_model.debug_read(k[4:], B, C, L).cpu()[:, ::TAP_CSTRIDE, ::TAP_LSTRIDE]
+        report.append(f"{k[4:]}: {rel_l2(got, g[k]):.2e}")
+    e2, em = rel_l2(eps, g["eps"]), max_abs_rel(eps, g["eps"])
+    print(f"{name}: eps rel-L2 {e2:.3e} max-abs/max-ref {em:.3e}; taps {report}")
+    assert_close(eps, torch.from_numpy(g["eps"]), f"{name} eps (taps: {report})")
+    for k in (k for k in g if k.startswith("tap_")):
+        C, L = lv[k[4:]]
+        got = model.diffusion_model.debug_read(k[4:], B, C, L).cpu()[:, ::TAP_CSTRIDE, ::TAP_LSTRIDE]
+        assert_close(got, torch.from_numpy(g[k]), f"{name} stage {k[4:]}")
+
+
+def test_stagewise_against_oracle_fresh_inputs():
+    """Every stage output of the tiny network vs the oracle on inputs no fixture
+    has seen; the first failing stage is named."""
+    cfg = TINY_UNET_CONFIG
+    model = model_for("tiny")
+    orc = Oracle(cfg, synth_state_dict(cfg, 0))
+    lv = stage_levels(cfg)
+    orc.capture = set(lv)
+    B = 3
+    x, cond, ic, t = synth_inputs(B, seed=23, image_cond_len=1536, t=[0, 999, 417])
+    ref = orc.forward(x, cond, ic, t)
+    eps = run(model, x, cond, ic, t)
+    order = [f"in{i}" for i in range(len(build_arch(**cfg).input_stages))] + ["mid"] + \
+            [f"out{i}" for i in range(len(build_arch(**cfg).output_stages))]
+    errs = []
+    for k in order:
+        C, L = lv[k]
+        got = model.diffusion_model.debug_read(k, B, C, L).cpu()
+        errs.append((k, rel_l2(got, orc.taps[k]), max_abs_rel(got, orc.taps[k])))
+    print("stage errors:", [(k, f"{a:.1e}") for k, a, _ in errs])
+    for k, a, m in errs:
+        assert a <= 1e-3 and m <= 1e-3, f"first failing stage {k}: rel-L2 {a:.3e} max {m:.3e}; all: {errs}"
+    assert_close(eps, ref, "tiny eps vs oracle")
+
+
+def test_eager_capture_replay_are_bit_identical():
+    model = model_for("tiny", wseed=4)     # fresh handle: 1st call eager, 2nd captures, 3rd+ replays the graph
+    x, cond, ic, t = synth_inputs(2, seed=31, t=[10, 700])
+    outs = [run(model, x, cond, ic, t) for _ in range(4)]
+    for o in outs[1:]:
+        assert torch.equal(o, outs[0])
+    x2, cond2, ic2, t2 = synth_inputs(2, seed=32, t=[11, 3])
+    a = run(model, x2, cond2, ic2, t2)      # graph replay with different caller buffers
+    b = run(copy.deepcopy(model), x2, cond2, ic2, t2)   # a deep copy builds its own engine; first call is eager
+    assert torch.equal(a, b)
+
+
+def test_batch_independence_full_config():
+    """Nothing in the UNet mixes samples (GroupNorm is per sample, attention per
+    sample): a batch equals its samples run alone, up to split-K summation order."""
+    model = model_for("base")
+    B = 4
+    x, cond, ic, t = synth_inputs(B, seed=41, t=[999, 500, 250, 0])
+    full = run(model, x, cond, ic, t)
+    assert bool(torch.isfinite(full).all())
+    for b in (0, 3):
+        one = run(model, x[b:b + 1], cond[b:b + 1], ic[b:b + 1], t[b:b + 1])
+        assert_close(full[b:b + 1], one, f"sample {b} of batch vs alone", tol_l2=2e-5, tol_max=2e-5)
+
+
+def test_image_cond_only_xy_plane_is_read():
+    """unet.py:1024 keeps image_cond[:, :, :1024] and zero-fills the rest."""
+    model = model_for("tiny")
+    x, cond, ic, t = synth_inputs(1, seed=51, image_cond_len=2048)
+    a = run(model, x, cond, ic, t)
+    b = run(model, x, cond, ic[:, :, :1024].contiguous(), t)
+    ic2 = ic.clone(); ic2[:, :, 1024:] = 1e3
+    c = run(model, x, cond, ic2, t)
+    assert torch.equal(a, b) and torch.equal(a, c)
+
+
+def test_argument_errors_surface_as_runtime_errors():
+    model = model_for("tiny")
+    x, cond, ic, t = synth_inputs(2)
+    with pytest.raises(RuntimeError):
+        model(x.to(DEV)[:, :3], cond.to(DEV), ic.to(DEV), t.to(DEV))
+    with pytest.raises(RuntimeError):
+        model(x.to(DEV), cond.to(DEV), ic.to(DEV)[:, :, :512], t.to(DEV))
+    with pytest.raises(RuntimeError):
+        model(x.to(DEV), cond.to(DEV), ic.to(DEV), t.to(DEV)[:1])
+    lib, h = model.diffusion_model.native_handle()
+    w = torch.zeros(7, device=DEV)
+    shape = (ctypes.c_int64 * 1)(7)
+    assert lib.mtv_load_weight(h, b"diffusion_model.not_a_key", ctypes.c_void_p(w.data_ptr()), shape, 1, None, None) != 0
+    assert b"unexpected key" in lib.mtv_last_error()
+    assert lib.mtv_load_weight(h, b"out.0.weight", ctypes.c_void_p(w.data_ptr()), shape, 1, None, None) != 0
+    assert b"size mismatch" in lib.mtv_last_error()
+    used = ctypes.c_int32(5)
+    big = torch.zeros(1, 4, 2048, device=DEV)
+    shp = (ctypes.c_int64 * 3)(1, 4, 2048)
+    assert lib.mtv_load_weight(h, b"zeros", ctypes.c_void_p(big.data_ptr()), shp, 3, ctypes.byref(used), None) == 0
+    assert used.value == 0    # dead keys are accepted and ignored
+
+
+def test_missing_weight_is_reported():
+    cfg = TINY_UNET_CONFIG
+    um = UNetModel(**cfg).to(DEV).eval()
+    lib = _lib.load_library()
+    c = _lib.MtvConfig()
+    c.abi_version, c.image_size, c.in_channels, c.out_channels = _lib.MTV_ABI_VERSION, 32, 4, 4
+    c.model_channels, c.num_res_blocks, c.num_heads, c.num_levels = 64, 1, 4, 2
+    c.channel_mult[0], c.channel_mult[1] = 1, 2
+    c.attn_at_level[0], c.attn_at_level[1] = 1, 1
+    c.device = 0
+    h = ctypes.c_void_p()
+    assert lib.mtv_create(ctypes.byref(c), ctypes.byref(h)) == 0
+    need, miss = ctypes.c_int32(), ctypes.c_int32()
+    assert lib.mtv_weights_ready(h, ctypes.byref(need), ctypes.byref(miss)) != 0
+    assert need.value == miss.value > 0 and b"missing key" in lib.mtv_last_error()
+    x = torch.zeros(1, 4, 2048, device=DEV); cd = torch.zeros(1, 8, 2048, device=DEV)
+    t = torch.zeros(1, dtype=torch.long, device=DEV); out = torch.empty(1, 4, 2048, device=DEV)
+    rc = lib.mtv_unet_forward(h, x.data_ptr(), cd.data_ptr(), x.data_ptr(), 2048, t.data_ptr(), 1, out.data_ptr(), None)
+    assert rc != 0 and b"weight not loaded" in lib.mtv_last_error()
+    assert lib.mtv_destroy(h) == 0
+    del um
+
+
+# ----------------------------------------------------------------------------- sampler
+def test_ddim_step_and_q_sample_are_bit_exact():
+    model = model_for("tiny")
+    ddpm = DDPM(model, channels=4, image_size=32, sampling_timesteps=100, w=0.0).to(DEV)
+    s = schedule()
+    lib, h = model.diffusion_model.native_handle()
+    g = torch.Generator().manual_seed(9)
+    img, eps, nz = (torch.randn(2, 4, 2048, generator=g) * sc for sc in (1.0, 1.0, 1.0))
+    for time, tn in ((999, 989), (509, 499), (19, 9), (9, -1)):
+        want = ddim_update(img.clone(), eps, nz, s, time, tn)
+        d_img = img.to(DEV).clone()
+        sr, srm1, san, c, sigma = ddpm.step_scalars(time, tn)
+        rc = lib.mtv_ddim_step(h, d_img.data_ptr(), eps.to(DEV).data_ptr(), nz.to(DEV).data_ptr(), d_img.numel(),
+                               sr, srm1, san, c, sigma, 1 if tn < 0 else 0, None)
+        assert rc == 0
+        torch.cuda.synchronize()
+        assert torch.equal(d_img.cpu(), want), f"ddim step ({time},{tn}) differs"
+    t = torch.tensor([250], device=DEV)
+    q = ddpm.q_sample(img.to(DEV), t, nz.to(DEV)).cpu()
+    want = s["sqrt_alphas_cumprod"][250] * img + s["sqrt_one_minus_alphas_cumprod"][250] * nz
+    assert torch.equal(q, want)
+
+
+@pytest.mark.parametrize("name", ["ddim_tiny_s10", "ddim_tiny_noised", "ddim_base_s50", "ddim_base_noised_r25"])
+def test_ddim_trajectory_matches_reference_fixture(name):
+    """Whole sampling loops (DDPM.sample of the reference, CPU) vs the CUDA loop,
+    with the reference's noise replayed from the same global CPU generator."""
+    g = load_golden(name)
+    model = model_for(str(g["config"]), int(g["wseed"]))
+    B, S = int(g["B"]), int(g["S"])
+    x, cond, ic, _ = synth_inputs(B, int(g["iseed"]), int(g["ic_len"]), 0)
+    ddpm = DDPM(model, channels=4, image_size=32, sampling_timesteps=S, w=0.0).to(DEV)
+    ddpm.noise_fn = lambda kind, shape, device: torch.randn(shape).to(device)
+    torch.manual_seed(int(g["nseed"]))
+    if bool(g["noised"]):
+        z = ddpm.sample(batch_size=B, cond=cond.to(DEV), image_cond=ic.to(DEV), noised_start=torch.tanh(x).to(DEV),
+                        ratio_=float(g["ratio"]), fix_noise=bool(g["fix_noise"]))
+    else:
+        z = ddpm.sample(batch_size=B, cond=cond.to(DEV), image_cond=ic.to(DEV))
+    torch.cuda.synchronize()
+    e2, em = rel_l2(z, g["z"]), max_abs_rel(z, g["z"])
+    print(f"{name}: final latent rel-L2 {e2:.3e} max-abs/max-ref {em:.3e}")
+    assert_close(z.cpu(), torch.from_numpy(g["z"]), f"{name} final latent")
+
+
+def test_sampler_properties_full_size():
+    """Config-3-sized run (4 chunks in one batch, 100-step schedule truncated to the
+    default ratio 0.25 = 25 steps): finite, clamped to [-1,1] by the final step,
+    deterministic under a fixed CUDA seed, and per-chunk independent."""
+    model = model_for("base")
+    B = 4
+    x, cond, ic, _ = synth_inputs(B, seed=61)
+    ddpm = DDPM(model, channels=4, image_size=32, sampling_timesteps=100, w=0.0).to(DEV)
+    args = dict(cond=cond.to(DEV), image_cond=ic.to(DEV), noised_start=torch.tanh(x).to(DEV), ratio_=0.25, fix_noise=True)
+    z1 = ddpm.sample(batch_size=B, **args)
+    z2 = ddpm.sample(batch_size=B, **args)
+    torch.cuda.synchronize()
+    assert tuple(z1.shape) == (B, 4, 2048) and bool(torch.isfinite(z1).all())
+    assert float(z1.abs().max()) <= 1.0
+    assert torch.equal(z1, z2)
