@@ -276,9 +276,11 @@ int conv_simt_pick_ksplit(const ConvParams& P, int num_sms) {
 
 cudaError_t launch_conv_simt(const ConvParams& P, cudaStream_t s) {
   const int M = P.B * P.geo.L;
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0; cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  }
   const int ks = P.ksplit > 1 ? P.ksplit : 1;
   if (P.Cout <= 16) {
     dim3 grid((M + 63) / 64, (P.Cout + 15) / 16, ks);

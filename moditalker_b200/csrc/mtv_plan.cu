@@ -156,6 +156,11 @@ struct MtvHandle_t {
   std::map<int, std::unique_ptr<Plan>> plans;
   Plan* last_plan = nullptr;
   int64_t weight_bytes = 0;
+  cudaStream_t cap_stream = nullptr;
+  cudaStream_t capture_stream() {
+    if (!cap_stream) CK(cudaStreamCreateWithFlags(&cap_stream, cudaStreamNonBlocking));
+    return cap_stream;
+  }
 
   float* dalloc(size_t bytes) {
     void* p = nullptr; CK(cudaMalloc(&p, bytes)); allocs.push_back(p); return (float*)p;
@@ -536,9 +541,12 @@ void forward(MtvHandle_t* h, const RunCtx& ctx, int B, cudaStream_t s) {
       if (pl->runs == 0) {
         run_ops(pl, 1, s);     // first call runs eagerly (function attributes, lazy module load)
       } else {
-        CK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-        try { run_ops(pl, 1, s); } catch (...) { cudaGraph_t g; cudaStreamEndCapture(s, &g); throw; }
-        CK(cudaStreamEndCapture(s, &pl->graph));
+        // capture on a private stream: the caller's stream may be the legacy default stream,
+        // which cannot be captured
+        cudaStream_t cs = h->capture_stream();
+        CK(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+        try { run_ops(pl, 1, cs); } catch (...) { cudaGraph_t g = nullptr; cudaStreamEndCapture(cs, &g); if (g) cudaGraphDestroy(g); throw; }
+        CK(cudaStreamEndCapture(cs, &pl->graph));
         CK(cudaGraphInstantiate(&pl->exec, pl->graph, 0));
         CK(cudaGraphLaunch(pl->exec, s));
       }
@@ -605,6 +613,7 @@ int mtv_destroy(MtvHandle h) {
     cudaSetDevice(h->cfg.device);
     cudaDeviceSynchronize();
     h->plans.clear();
+    if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
     for (void* p : h->allocs) cudaFree(p);
     delete h;
   });

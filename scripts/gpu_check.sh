@@ -15,7 +15,7 @@ cat gpurun_out/bench.json; tail -n 5 gpurun_out/bench.err
 if [ "${1:-}" != "quick" ]; then
   timeout 600 python bench.py --chunks-per-gpu 8 --no-cpu-baseline > gpurun_out/bench_b8.json 2>> gpurun_out/bench.err
   cat gpurun_out/bench_b8.json
-  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/launches.csv \
-      python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"k_(conv|attn|gn_|splitk|linear|temb|pack|ddim|apply|tc_)" -c 3000 --csv --log-file gpurun_out/launches.csv \
+      env MTV_NO_GRAPH=1 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
   echo "ncu rc=$?" | tee -a gpurun_out/summary.txt
 fi
