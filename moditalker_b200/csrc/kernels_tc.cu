@@ -1,0 +1,461 @@
+// kernels_tc.cu — tcgen05 / TMA tensor-core kernels (sm_100a only).
+//
+//   k_apply_split : y = silu?(x*a + d) (GroupNorm affine [+FiLM] produced by k_gn_stats),
+//                   optional nearest-x2 / avgpool-2x2 resample, optional channel concat of
+//                   two sources, written as a SPLIT-BF16 pair (hi = bf16(y), lo = bf16(y - hi))
+//                   token-major [B][L][C] — the A operand of the tap-GEMM below.
+//   k_conv_tc     : implicit-GEMM 3x3 / 1x1 convolution on the 5th-gen tensor cores.
+//                   D[128 tokens x BN couts] (fp32, TMEM) += A_tap[128 x 64] * W_tap[BN x 64]^T
+//                   for every tap and 64-channel chunk.  A tiles are TMA *spatial boxes* of the
+//                   token-major activation (one shifted box per tap; the conv's zero padding is
+//                   TMA out-of-bounds fill, so planes never bleed into each other), W tiles are
+//                   TMA boxes of the pre-split weights.  fp32-class accuracy from three bf16
+//                   MMAs per product:  A_hi*W_hi + A_lo*W_hi + A_hi*W_lo  (error ~2^-16 per
+//                   product instead of bf16's 2^-8; the MToV parity bar of 1e-3 rules out plain
+//                   bf16 and leaves single-pass TF32 no margin over a 50-step trajectory,
+//                   SURVEY.md §7).  Warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer
+//                   (+TMEM alloc), warps 2-5 = epilogue (tcgen05.ld -> +bias +residual -> HBM).
+//
+// Reference semantics: ResBlock._forward conv3x3s (unet.py:134,159,178-207), the 1x1
+// qkv / proj_out convs of AttentionBlock* (unet.py:234,242,251-254,297-300).
+#include "mtv_kernels.cuh"
+#include "mtv_tc.cuh"
+
+#include <cuda_bf16.h>
+
+namespace mtv {
+
+// ------------------------------------------------------------------ apply + split
+__device__ __forceinline__ float silu_tc(float v) { return v / (1.0f + __expf(-v)); }
+
+__device__ __forceinline__ void tc_decode_tok(const Geo& g, int tok, int& p, int& y, int& x) {
+  const int nxy = g.res * g.res;
+  if (tok < nxy) { p = 0; y = tok / g.res; x = tok - y * g.res; }
+  else { int r = tok - nxy; const int np = g.t * g.res; p = 1; if (r >= np) { p = 2; r -= np; } y = r / g.res; x = r - y * g.res; }
+}
+__device__ __forceinline__ int tc_plane_off(const Geo& g, int p) { return p == 0 ? 0 : g.res * g.res + (p - 1) * g.t * g.res; }
+
+__global__ void __launch_bounds__(256) k_apply_split(const __grid_constant__ ApplyParams P) {
+  const int C = P.C0 + P.C1;
+  const int cq = C >> 2;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)P.B * P.geo.L * cq;
+  if (idx >= total) return;
+  const int c = (int)(idx % cq) * 4;
+  const size_t m = idx / cq;
+  const int b = (int)(m / P.geo.L), tok = (int)(m - (size_t)b * P.geo.L);
+  int p, y, x; tc_decode_tok(P.geo, tok, p, y, x);
+  const float* src; int Cs, cc;
+  if (c < P.C0) { src = P.src0; Cs = P.C0; cc = c; } else { src = P.src1; Cs = P.C1; cc = c - P.C0; }
+  float4 na = make_float4(1.f, 1.f, 1.f, 1.f), nd = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (P.nrm_a) {
+    const size_t ni = ((size_t)b * P.nrm_nseg + (P.nrm_nseg == 3 ? p : 0)) * C + c;
+    na = __ldg(reinterpret_cast<const float4*>(P.nrm_a + ni));
+    nd = __ldg(reinterpret_cast<const float4*>(P.nrm_d + ni));
+  }
+  auto xf = [&](float4 v) {
+    if (P.nrm_a) { v.x = fmaf(v.x, na.x, nd.x); v.y = fmaf(v.y, na.y, nd.y); v.z = fmaf(v.z, na.z, nd.z); v.w = fmaf(v.w, na.w, nd.w); }
+    if (P.silu) { v.x = silu_tc(v.x); v.y = silu_tc(v.y); v.z = silu_tc(v.z); v.w = silu_tc(v.w); }
+    return v;
+  };
+  float4 v;
+  if (P.resample == RS_NONE) {
+    v = xf(__ldg(reinterpret_cast<const float4*>(src + ((size_t)b * P.geo.L + tok) * Cs + cc)));
+  } else if (P.resample == RS_UP2) {
+    const Geo gs = geo_down(P.geo);
+    const int ts = tc_plane_off(gs, p) + (y >> 1) * gs.res + (x >> 1);
+    v = xf(__ldg(reinterpret_cast<const float4*>(src + ((size_t)b * gs.L + ts) * Cs + cc)));
+  } else {
+    const Geo gs = geo_up(P.geo);
+    const int ts = tc_plane_off(gs, p) + (2 * y) * gs.res + 2 * x;
+    const float* q = src + ((size_t)b * gs.L + ts) * Cs + cc;
+    const float4 v0 = xf(__ldg(reinterpret_cast<const float4*>(q)));
+    const float4 v1 = xf(__ldg(reinterpret_cast<const float4*>(q + Cs)));
+    const float4 v2 = xf(__ldg(reinterpret_cast<const float4*>(q + (size_t)gs.res * Cs)));
+    const float4 v3 = xf(__ldg(reinterpret_cast<const float4*>(q + (size_t)(gs.res + 1) * Cs)));
+    v.x = 0.25f * ((v0.x + v1.x) + (v2.x + v3.x)); v.y = 0.25f * ((v0.y + v1.y) + (v2.y + v3.y));
+    v.z = 0.25f * ((v0.z + v1.z) + (v2.z + v3.z)); v.w = 0.25f * ((v0.w + v1.w) + (v2.w + v3.w));
+  }
+  const float f[4] = {v.x, v.y, v.z, v.w};
+  __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    hi[i] = __float2bfloat16_rn(f[i]);
+    lo[i] = __float2bfloat16_rn(f[i] - __bfloat162float(hi[i]));
+  }
+  const size_t o = m * C + c;
+  *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(P.hi) + o) = *reinterpret_cast<const uint2*>(hi);
+  *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(P.lo) + o) = *reinterpret_cast<const uint2*>(lo);
+}
+
+cudaError_t launch_apply_split(const ApplyParams& P, cudaStream_t s) {
+  const size_t total = (size_t)P.B * P.geo.L * ((P.C0 + P.C1) / 4);
+  k_apply_split<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(P);
+  return cudaGetLastError();
+}
+
+// fp32 [rows][cols] -> split bf16 pair (weights, once at load time)
+__global__ void k_split_bf16(const float* __restrict__ src, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = src[i];
+  const __nv_bfloat16 h = __float2bfloat16_rn(v);
+  hi[i] = h; lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+// PyTorch conv weight [Cout][Cin][taps] -> K-major split-bf16 [taps][Cout][Cin]
+__global__ void k_repack_split_w(const float* __restrict__ src, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                                 int Cout, int Cin, int taps) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)Cout * Cin * taps) return;
+  const int ci = (int)(i % Cin);
+  const int co = (int)((i / Cin) % Cout);
+  const int tp = (int)(i / ((size_t)Cin * Cout));
+  const float v = src[((size_t)co * Cin + ci) * taps + tp];
+  const __nv_bfloat16 h = __float2bfloat16_rn(v);
+  hi[i] = h; lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+cudaError_t launch_repack_split_w(const float* src, void* hi, void* lo, int Cout, int Cin, int taps, cudaStream_t s) {
+  const size_t n = (size_t)Cout * Cin * taps;
+  k_repack_split_w<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(src, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, Cout, Cin, taps);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+               ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+               ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const void* tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, 128-byte-swizzled operand tile: rows of 64 bf16 (128 B), 8-row groups 1024 B apart.
+// Bit layout: cute/arch/mma_sm100_desc.hpp SmemDescriptor (start>>4 [0,14), LBO>>4 [16,30),
+// SBO>>4 [32,46), version=1 [46,48), layout SWIZZLE_128B=2 [61,64)).
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;                  // LBO (ignored for swizzled K-major; canonical value 1)
+  d |= (uint64_t)(1024 >> 4) << 32;        // SBO = 8 rows * 128 B
+  d |= (uint64_t)1 << 46;                  // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                  // SWIZZLE_128B
+  return d;
+}
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major (InstrDescriptor bit-fields).
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ------------------------------------------------------------------ the tap-GEMM
+constexpr int TC_BM = 128, TC_BK = 64, TC_THREADS = 192;
+__host__ __device__ constexpr int tc_stage_bytes(int BN) { return 2 * TC_BM * 128 + 2 * BN * 128; }
+__host__ __device__ constexpr int tc_stages(int BN) { return BN == 64 ? 4 : 3; }
+__host__ __device__ constexpr int tc_smem_bytes(int BN) { return tc_stages(BN) * tc_stage_bytes(BN) + 1024; }
+
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant__ TcConvParams P) {
+  constexpr int NS = tc_stages(BN);
+  constexpr int STAGE = tc_stage_bytes(BN);
+  constexpr uint32_t IDESC = umma_idesc_bf16(TC_BM, BN);
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_full[NS], bar_empty[NS], bar_acc;
+  __shared__ uint32_t tmem_base_s;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B tiles need 1024-B alignment
+
+  const Geo g = P.geo;
+  const int n0 = blockIdx.y * BN;
+  // ---- which 128 tokens does this CTA own?
+  const int tile = blockIdx.x;
+  const int tps = g.L / TC_BM;                       // tiles per sample (16, 4, 1)
+  const int b = tile / tps, tl = tile - b * tps;
+  const int tok0 = tl * TC_BM;
+
+  // K range of this CTA (split-K over the flattened (tap, 64-channel chunk) space)
+  const int kch = P.Cin / TC_BK;
+  const int it_main = P.taps * kch;
+  const int it_total = it_main + P.Cin2 / TC_BK;
+  int it0 = 0, it1 = it_total;
+  if (P.ksplit > 1) {
+    const int per = (it_total + P.ksplit - 1) / P.ksplit;
+    it0 = blockIdx.z * per; it1 = min(it_total, it0 + per);
+  }
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NS; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
+    mbar_init(&bar_acc, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    prefetch_tmap(&P.tmA_hi[0]); prefetch_tmap(&P.tmA_lo[0]); prefetch_tmap(&P.tmW_hi); prefetch_tmap(&P.tmW_lo);
+    if (P.taps == 9) { prefetch_tmap(&P.tmA_hi[1]); prefetch_tmap(&P.tmA_lo[1]); }
+    if (P.Cin2) { prefetch_tmap(&P.tmA2_hi); prefetch_tmap(&P.tmA2_lo); prefetch_tmap(&P.tmW2_hi); prefetch_tmap(&P.tmW2_lo); }
+  }
+  if (warp == 1) {   // TMEM: BN fp32 accumulator columns x 128 lanes
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"((uint32_t)BN) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int it = it0; it < it1; ++it) {
+        mbar_wait(&bar_empty[stage], phase ^ 1u);
+        mbar_expect_tx(&bar_full[stage], (uint32_t)STAGE);
+        const uint32_t sA_hi = smem0 + stage * STAGE, sA_lo = sA_hi + TC_BM * 128;
+        const uint32_t sW_hi = sA_lo + TC_BM * 128, sW_lo = sW_hi + BN * 128;
+        const uint32_t fb = smem_u32(&bar_full[stage]);
+        if (it >= it_main) {           // second K-segment: 1x1 conv of the skip operand
+          const int c2 = (it - it_main) * TC_BK;
+          const int row = b * g.L + tok0;
+          tma_load_2d(sA_hi, &P.tmA2_hi, fb, c2, row);
+          tma_load_2d(sA_lo, &P.tmA2_lo, fb, c2, row);
+          tma_load_2d(sW_hi, &P.tmW2_hi, fb, c2, n0);
+          tma_load_2d(sW_lo, &P.tmW2_lo, fb, c2, n0);
+          if (++stage == NS) { stage = 0; phase ^= 1u; }
+          continue;
+        }
+        const int tap = it / kch, kc = it - tap * kch;
+        const int c0 = kc * TC_BK;
+        if (P.taps == 1) {
+          const int row = b * g.L + tok0;
+          tma_load_2d(sA_hi, &P.tmA_hi[0], fb, c0, row);
+          tma_load_2d(sA_lo, &P.tmA_lo[0], fb, c0, row);
+        } else {
+          const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
+          const int nxy = g.res * g.res, npl = g.t * g.res;
+          if (g.L == TC_BM) {
+            // level with 128 tokens per sample: the tile is the whole sample = three boxes
+            // (xy: res rows, yt / xt: t rows each), stacked in token order
+            tma_load_4d(sA_hi, &P.tmA_hi[0], fb, c0, dx, dy, b);
+            tma_load_4d(sA_lo, &P.tmA_lo[0], fb, c0, dx, dy, b);
+            tma_load_5d(sA_hi + nxy * 128, &P.tmA_hi[1], fb, c0, dx, dy, 0, b);
+            tma_load_5d(sA_lo + nxy * 128, &P.tmA_lo[1], fb, c0, dx, dy, 0, b);
+            tma_load_5d(sA_hi + (nxy + npl) * 128, &P.tmA_hi[1], fb, c0, dx, dy, 1, b);
+            tma_load_5d(sA_lo + (nxy + npl) * 128, &P.tmA_lo[1], fb, c0, dx, dy, 1, b);
+          } else if (tok0 < nxy) {
+            const int y0 = tok0 / g.res;
+            tma_load_4d(sA_hi, &P.tmA_hi[0], fb, c0, dx, y0 + dy, b);
+            tma_load_4d(sA_lo, &P.tmA_lo[0], fb, c0, dx, y0 + dy, b);
+          } else {
+            const int r = tok0 - nxy;
+            const int pl = r / npl, y0 = (r - pl * npl) / g.res;
+            tma_load_5d(sA_hi, &P.tmA_hi[1], fb, c0, dx, y0 + dy, pl, b);
+            tma_load_5d(sA_lo, &P.tmA_lo[1], fb, c0, dx, y0 + dy, pl, b);
+          }
+        }
+        tma_load_2d(sW_hi, &P.tmW_hi, fb, c0, tap * P.Cout + n0);
+        tma_load_2d(sW_lo, &P.tmW_lo, fb, c0, tap * P.Cout + n0);
+        if (++stage == NS) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer =================================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int it = it0; it < it1; ++it) {
+        mbar_wait(&bar_full[stage], phase);
+        tc_fence_after();
+        const uint32_t sA_hi = smem0 + stage * STAGE, sA_lo = sA_hi + TC_BM * 128;
+        const uint32_t sW_hi = sA_lo + TC_BM * 128, sW_lo = sW_hi + BN * 128;
+#pragma unroll
+        for (int k = 0; k < TC_BK / 16; ++k) {
+          const uint64_t a_hi = umma_desc_sw128(sA_hi + k * 32), a_lo = umma_desc_sw128(sA_lo + k * 32);
+          const uint64_t w_hi = umma_desc_sw128(sW_hi + k * 32), w_lo = umma_desc_sw128(sW_lo + k * 32);
+          umma_bf16(tmem_base, a_hi, w_hi, IDESC, (it > it0 || k > 0) ? 1u : 0u);
+          umma_bf16(tmem_base, a_lo, w_hi, IDESC, 1u);
+          umma_bf16(tmem_base, a_hi, w_lo, IDESC, 1u);
+        }
+        umma_commit(&bar_empty[stage]);          // frees the smem slot once these MMAs have read it
+        if (++stage == NS) { stage = 0; phase ^= 1u; }
+      }
+      umma_commit(&bar_acc);                      // accumulator complete
+    }
+  } else {
+    // =============================== epilogue ===================================
+    const int q = warp & 3;                       // TMEM lane quarter this warp may read
+    const int row = q * 32 + lane;                // token within the tile
+    const int tok = tok0 + row;
+    const size_t m = (size_t)b * g.L + tok;
+    mbar_wait(&bar_acc, 0);
+    tc_fence_after();
+    int p = 0, y = 0, x = 0;
+    if (P.resid && P.resid_mode != RS_NONE) tc_decode_tok(g, tok, p, y, x);
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+      const int n = n0 + c0;
+      if (P.ksplit > 1) {
+        float* dst = P.partial + ((size_t)blockIdx.z * ((size_t)P.B * g.L) + m) * P.Cout + n;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                            __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+      } else {
+        float* dst = P.out + m * P.Cout + n;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+          if (P.bias) {
+            const float4 bv = __ldg(reinterpret_cast<const float4*>(P.bias + n + j));
+            v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+          }
+          if (P.resid) {
+            if (P.resid_mode == RS_NONE) {
+              const float4 rv = __ldg(reinterpret_cast<const float4*>(P.resid + m * P.Cout + n + j));
+              v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
+            } else if (P.resid_mode == RS_UP2) {
+              const Geo gs = geo_down(g);
+              const int ts = tc_plane_off(gs, p) + (y >> 1) * gs.res + (x >> 1);
+              const float4 rv = __ldg(reinterpret_cast<const float4*>(P.resid + ((size_t)b * gs.L + ts) * P.Cout + n + j));
+              v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
+            } else {
+              const Geo gs = geo_up(g);
+              const int t0 = tc_plane_off(gs, p) + (2 * y) * gs.res + 2 * x;
+              const float* rp = P.resid + ((size_t)b * gs.L + t0) * P.Cout + n + j;
+              const float4 r0 = __ldg(reinterpret_cast<const float4*>(rp));
+              const float4 r1 = __ldg(reinterpret_cast<const float4*>(rp + P.Cout));
+              const float4 r2 = __ldg(reinterpret_cast<const float4*>(rp + (size_t)gs.res * P.Cout));
+              const float4 r3 = __ldg(reinterpret_cast<const float4*>(rp + (size_t)(gs.res + 1) * P.Cout));
+              v.x += 0.25f * (r0.x + r1.x + r2.x + r3.x); v.y += 0.25f * (r0.y + r1.y + r2.y + r3.y);
+              v.z += 0.25f * (r0.z + r1.z + r2.z + r3.z); v.w += 0.25f * (r0.w + r1.w + r2.w + r3.w);
+            }
+          }
+          *reinterpret_cast<float4*>(dst + j) = v;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+  }
+}
+
+// split-K epilogue for the tensor-core path (fixed summation order)
+__global__ void k_tc_splitk_epilogue(const __grid_constant__ TcConvParams P) {
+  const Geo g = P.geo;
+  const size_t M = (size_t)P.B * g.L;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int nq = P.Cout >> 2;
+  if (idx >= M * nq) return;
+  const size_t m = idx / nq; const int n = (int)(idx - m * nq) * 4;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int z = 0; z < P.ksplit; ++z) {
+    const float4 v = *reinterpret_cast<const float4*>(P.partial + ((size_t)z * M + m) * P.Cout + n);
+    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+  }
+  if (P.bias) { const float4 bv = __ldg(reinterpret_cast<const float4*>(P.bias + n)); s.x += bv.x; s.y += bv.y; s.z += bv.z; s.w += bv.w; }
+  if (P.resid) {
+    const int b = (int)(m / g.L), tok = (int)(m - (size_t)b * g.L);
+    if (P.resid_mode == RS_NONE) {
+      const float4 rv = __ldg(reinterpret_cast<const float4*>(P.resid + m * P.Cout + n));
+      s.x += rv.x; s.y += rv.y; s.z += rv.z; s.w += rv.w;
+    } else {
+      int p, y, x; tc_decode_tok(g, tok, p, y, x);
+      if (P.resid_mode == RS_UP2) {
+        const Geo gs = geo_down(g);
+        const int ts = tc_plane_off(gs, p) + (y >> 1) * gs.res + (x >> 1);
+        const float4 rv = __ldg(reinterpret_cast<const float4*>(P.resid + ((size_t)b * gs.L + ts) * P.Cout + n));
+        s.x += rv.x; s.y += rv.y; s.z += rv.z; s.w += rv.w;
+      } else {
+        const Geo gs = geo_up(g);
+        const int t0 = tc_plane_off(gs, p) + (2 * y) * gs.res + 2 * x;
+        const float* rp = P.resid + ((size_t)b * gs.L + t0) * P.Cout + n;
+        const float4 r0 = __ldg(reinterpret_cast<const float4*>(rp));
+        const float4 r1 = __ldg(reinterpret_cast<const float4*>(rp + P.Cout));
+        const float4 r2 = __ldg(reinterpret_cast<const float4*>(rp + (size_t)gs.res * P.Cout));
+        const float4 r3 = __ldg(reinterpret_cast<const float4*>(rp + (size_t)(gs.res + 1) * P.Cout));
+        s.x += 0.25f * (r0.x + r1.x + r2.x + r3.x); s.y += 0.25f * (r0.y + r1.y + r2.y + r3.y);
+        s.z += 0.25f * (r0.z + r1.z + r2.z + r3.z); s.w += 0.25f * (r0.w + r1.w + r2.w + r3.w);
+      }
+    }
+  }
+  *reinterpret_cast<float4*>(P.out + m * P.Cout + n) = s;
+}
+
+cudaError_t launch_conv_tc(const TcConvParams& P, cudaStream_t s) {
+  const int BN = P.bn;
+  if ((BN != 64 && BN != 128) || P.Cout % BN || (P.B * P.geo.L) % TC_BM || P.Cin % TC_BK || P.Cin2 % TC_BK)
+    return cudaErrorInvalidValue;
+  const int M = P.B * P.geo.L;
+  dim3 grid(M / TC_BM, P.Cout / BN, P.ksplit > 1 ? P.ksplit : 1);
+  cudaError_t e;
+  if (BN == 64) {
+    e = cudaFuncSetAttribute(k_conv_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(64));
+    if (e != cudaSuccess) return e;
+    k_conv_tc<64><<<grid, TC_THREADS, tc_smem_bytes(64), s>>>(P);
+  } else {
+    e = cudaFuncSetAttribute(k_conv_tc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(128));
+    if (e != cudaSuccess) return e;
+    k_conv_tc<128><<<grid, TC_THREADS, tc_smem_bytes(128), s>>>(P);
+  }
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  if (P.ksplit > 1) {
+    const size_t tot = (size_t)M * (P.Cout / 4);
+    k_tc_splitk_epilogue<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(P);
+    e = cudaGetLastError();
+  }
+  return e;
+}
+
+}  // namespace mtv

@@ -8,6 +8,7 @@
 // kernels.
 #include "../../include/mtv_b200.h"
 #include "mtv_kernels.cuh"
+#include "mtv_tc.cuh"
 
 #include <cmath>
 #include <cstdio>
@@ -115,6 +116,7 @@ enum { WK_PLAIN = 0, WK_CONV = 1 };
 struct Weight {
   std::string name; std::vector<int64_t> shape; size_t elems = 0;
   float* dev = nullptr; bool owned = true; bool loaded = false; int kind = WK_PLAIN;
+  void* hi = nullptr; void* lo = nullptr;   // split-bf16 K-major copy [taps][Cout][Cin] for the tcgen05 path
 };
 
 struct Tensor { float* p = nullptr; int C = 0; int level = 0; };
@@ -152,10 +154,12 @@ struct MtvHandle_t {
   std::vector<void*> allocs;
   float* emb_wall = nullptr; float* emb_ball = nullptr; float* freqs = nullptr;
   std::unordered_map<std::string, float*> bias_sum;   // ResBlock name -> conv2.bias + skip.bias
+  std::unordered_map<const float*, std::pair<void*, void*>> tc_w;   // fp32 conv weight -> split-bf16 pair
   bool dirty = true; bool use_graph = true;
   std::map<int, std::unique_ptr<Plan>> plans;
   Plan* last_plan = nullptr;
   int64_t weight_bytes = 0;
+  int tc_mask = 0x3f;
   cudaStream_t cap_stream = nullptr;
   cudaStream_t capture_stream() {
     if (!cap_stream) CK(cudaStreamCreateWithFlags(&cap_stream, cudaStreamNonBlocking));
@@ -169,6 +173,10 @@ struct MtvHandle_t {
     Weight w; w.name = name; w.shape = shape; w.kind = kind; w.elems = 1;
     for (auto d : shape) w.elems *= (size_t)d;
     if (view) { w.dev = view; w.owned = false; } else { w.dev = dalloc(w.elems * sizeof(float)); }
+    if (kind == WK_CONV && cfg.kernel_path != 1 && shape[0] % 64 == 0 && shape[1] % 64 == 0) {
+      w.hi = dalloc(w.elems * 2); w.lo = dalloc(w.elems * 2);
+      tc_w[w.dev] = std::make_pair(w.hi, w.lo);
+    }
     weight_bytes += (int64_t)w.elems * 4;
     windex[name] = (int)weights.size(); weights.push_back(w);
     return (int)weights.size() - 1;
@@ -255,6 +263,33 @@ void ensure_ready(MtvHandle_t* h, cudaStream_t s) {
   h->dirty = false;
 }
 
+// ------------------------------------------------------------------ TMA descriptors
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr; cudaDriverEntryPointQueryResult q;
+    CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+    if (!p || q != cudaDriverEntryPointSuccess) throw MtvError("cuTensorMapEncodeTiled entry point unavailable");
+    fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+// bf16 tensor, innermost dimension contiguous, 128-byte swizzle, zero fill out of bounds
+CUtensorMap make_tmap_bf16(void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box) {
+  CUtensorMap m;
+  cuuint64_t gd[5]; cuuint64_t gs[4]; cuuint32_t bx[5]; cuuint32_t es[5];
+  for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
+  CUresult r = encode_tiled_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, base, gd, gs, bx, es,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw MtvError("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+  return m;
+}
+
 // ------------------------------------------------------------------ plan builder
 struct NormRef { float* a = nullptr; float* d = nullptr; int nseg = 0; };
 
@@ -302,8 +337,107 @@ struct Builder {
     return NormRef{P.nrm_a, P.nrm_d, P.nseg};
   }
 
+  // ---- tensor-core lowering -------------------------------------------------------------
+  bool tc_ok(const ConvParams& P) const {
+    if (h->cfg.kernel_path == 1 || P.out_chmajor) return false;
+    if (P.geo.L % 128 || P.Cout % 64) return false;
+    {   // debug bisection mask (MTV_TC_MASK): which op classes may use the tensor-core kernel
+      const int level = P.geo.res == h->cfg.image_size ? 0 : (P.geo.res == h->cfg.image_size / 2 ? 1 : 2);
+      int cls = P.nsegs == 2 ? 4 : (P.seg[0].taps == 1 ? 3 : level);
+      if (!((h->tc_mask >> cls) & 1)) return false;
+    }
+    for (int s = 0; s < P.nsegs; ++s) {
+      const KSeg& S = P.seg[s];
+      if ((S.C0 + S.C1) % 64) return false;
+      if (h->tc_w.find(S.w) == h->tc_w.end()) return false;
+      if (s == 1 && S.taps != 1) return false;
+    }
+    return true;
+  }
+  // split-bf16 operand of one K-segment + its TMA maps
+  void tc_operand(const std::string& name, const KSeg& S, const Geo& g, CUtensorMap* a_hi, CUtensorMap* a_lo) {
+    const int C = S.C0 + S.C1;
+    const size_t bytes = (size_t)B * g.L * C * 2;
+    void* hi = dalloc(bytes); void* lo = dalloc(bytes);
+    ApplyParams A{};
+    A.src0 = S.src0; A.src1 = S.src1; A.C0 = S.C0; A.C1 = S.C1; A.nrm_a = S.nrm_a; A.nrm_d = S.nrm_d; A.nrm_nseg = S.nrm_nseg;
+    A.silu = S.silu; A.resample = S.resample; A.B = B; A.geo = g; A.hi = hi; A.lo = lo;
+    Op op; op.name = "apply:" + name; op.bytes = (double)B * g.L * C * 8;
+    op.fn = [A](cudaStream_t s) { return launch_apply_split(A, s); };
+    pl->ops.push_back(op);
+    void* ptr[2] = {hi, lo}; CUtensorMap* dst[2] = {a_hi, a_lo};
+    for (int k = 0; k < 2; ++k) {
+      char* base = (char*)ptr[k];
+      if (S.taps == 1) {
+        const uint64_t dims[2] = {(uint64_t)C, (uint64_t)B * g.L}; const uint64_t str[1] = {(uint64_t)C * 2};
+        const uint32_t box[2] = {64, 128};
+        dst[k][0] = make_tmap_bf16(base, 2, dims, str, box);
+      } else {
+        const uint64_t rowb = (uint64_t)C * 2;
+        const uint32_t hb_xy = g.L == 128 ? (uint32_t)g.res : (uint32_t)(128 / g.res);
+        const uint32_t hb_pl = g.L == 128 ? (uint32_t)g.t : (uint32_t)(128 / g.res);
+        {
+          const uint64_t dims[4] = {(uint64_t)C, (uint64_t)g.res, (uint64_t)g.res, (uint64_t)B};
+          const uint64_t str[3] = {rowb, rowb * g.res, rowb * g.L};
+          const uint32_t box[4] = {64, (uint32_t)g.res, hb_xy, 1};
+          dst[k][0] = make_tmap_bf16(base, 4, dims, str, box);
+        }
+        {
+          const uint64_t dims[5] = {(uint64_t)C, (uint64_t)g.res, (uint64_t)g.t, 2, (uint64_t)B};
+          const uint64_t str[4] = {rowb, rowb * g.res, rowb * g.res * g.t, rowb * g.L};
+          const uint32_t box[5] = {64, (uint32_t)g.res, hb_pl, 1, 1};
+          dst[k][1] = make_tmap_bf16(base + rowb * g.res * g.res, 5, dims, str, box);
+        }
+      }
+    }
+  }
+  void conv_tc(const std::string& name, const ConvParams& P) {
+    TcConvParams T{};
+    const KSeg& S = P.seg[0];
+    T.taps = S.taps; T.Cin = S.C0 + S.C1; T.Cout = P.Cout; T.B = B; T.geo = P.geo;
+    T.bias = P.bias; T.resid = P.resid; T.resid_mode = P.resid_mode; T.out = P.out;
+    const int M = B * P.geo.L;
+    int bn = 64;
+    if (P.Cout % 128 == 0 && (M / 128) * (P.Cout / 128) >= h->num_sms) bn = 128;
+    T.bn = bn;
+    tc_operand(name, S, P.geo, T.tmA_hi, T.tmA_lo);
+    auto wmaps = [&](const KSeg& K, CUtensorMap& whi, CUtensorMap& wlo) {
+      const auto& pr = h->tc_w.at(K.w);
+      const int C = K.C0 + K.C1;
+      const uint64_t dims[2] = {(uint64_t)C, (uint64_t)K.taps * P.Cout}; const uint64_t str[1] = {(uint64_t)C * 2};
+      const uint32_t box[2] = {64, (uint32_t)bn};
+      whi = make_tmap_bf16(pr.first, 2, dims, str, box);
+      wlo = make_tmap_bf16(pr.second, 2, dims, str, box);
+    };
+    wmaps(S, T.tmW_hi, T.tmW_lo);
+    double Ktot = (double)S.taps * T.Cin;
+    if (P.nsegs == 2) {
+      const KSeg& X = P.seg[1];
+      T.Cin2 = X.C0 + X.C1;
+      tc_operand(name + ".skip", X, P.geo, &T.tmA2_hi, &T.tmA2_lo);
+      wmaps(X, T.tmW2_hi, T.tmW2_lo);
+      Ktot += T.Cin2;
+    }
+    const int iters = T.taps * (T.Cin / 64) + T.Cin2 / 64;
+    const int base = (M / 128) * (P.Cout / bn);
+    int ks = 1;
+    if (base < 64 && iters >= 32 && ((h->tc_mask >> 5) & 1)) {
+      ks = std::min(iters / 8, (128 + base - 1) / base);
+      ks = std::min(ks, 16);
+      while (ks > 1 && (ks - 1) * ((iters + ks - 1) / ks) >= iters) --ks;
+    }
+    T.ksplit = ks;
+    if (ks > 1) T.partial = (float*)dalloc((size_t)ks * M * P.Cout * sizeof(float));
+    Op op; op.name = "conv_tc:" + name; op.launches = ks > 1 ? 2 : 1;
+    op.flops = 2.0 * M * P.Cout * Ktot;
+    op.bytes = 4.0 * Ktot * P.Cout + 4.0 * M * Ktot / S.taps + 4.0 * M * P.Cout;
+    op.fn = [T](cudaStream_t s) { return launch_conv_tc(T, s); };
+    pl->ops.push_back(op);
+  }
+
   void conv(const std::string& name, ConvParams P, int phase = 1, bool out_is_ctx = false) {
     P.B = B;
+    if (phase == 1 && !out_is_ctx && tc_ok(P)) { conv_tc(name, P); return; }
     double K = 0;
     for (int s = 0; s < P.nsegs; ++s) {
       const int Ct = P.seg[s].C0 + P.seg[s].C1;
@@ -602,6 +736,7 @@ int mtv_create(const MtvConfig* cfg, MtvHandle* out) {
     h->arch = build_arch(*cfg);
     const char* ng = getenv("MTV_NO_GRAPH");
     h->use_graph = !(ng && ng[0] == '1');
+    if (const char* tm = getenv("MTV_TC_MASK")) h->tc_mask = (int)strtol(tm, nullptr, 0);
     register_weights(h.get());
     *out = h.release();
   });
@@ -641,6 +776,7 @@ int mtv_load_weight(MtvHandle h, const char* name, const float* data, const int6
       const int Cout = (int)w.shape[0], Cin = (int)w.shape[1];
       const int taps = (int)(w.elems / ((size_t)Cout * Cin));
       CK(launch_repack_conv(data, w.dev, Cout, Cin, taps, s));
+      if (w.hi) CK(launch_repack_split_w(data, w.hi, w.lo, Cout, Cin, taps, s));
     } else {
       CK(cudaMemcpyAsync(w.dev, data, w.elems * sizeof(float), cudaMemcpyDeviceToDevice, s));
     }

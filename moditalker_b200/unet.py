@@ -15,6 +15,7 @@ or CPU implementation of the forward in this package.
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Optional
 
 import torch
@@ -200,6 +201,9 @@ class UNetModel(nn.Module):
             _zero(nn.Conv2d(model_channels, out_channels, 3, padding=1)),
         )
         self._engine = _EngineSlot()
+        # 0 = tcgen05 tensor-core kernels wherever a tile shape exists (default);
+        # 1 = fp32 CUDA-core kernels everywhere (cross-check path used by the tests)
+        self.kernel_path = int(os.environ.get("MTV_KERNEL_PATH", "0"))
 
     # ------------------------------------------------------------------ weight sync
     def _apply(self, fn, *a, **k):
@@ -240,7 +244,7 @@ class UNetModel(nn.Module):
                 cfg.channel_mult[i] = int(m)
                 cfg.attn_at_level[i] = 1 if (1 << i) in self.attention_resolutions else 0
             cfg.device = device.index if device.index is not None else torch.cuda.current_device()
-            cfg.kernel_path = 0
+            cfg.kernel_path = int(self.kernel_path)
             h = ctypes.c_void_p()
             _lib.check(lib.mtv_create(ctypes.byref(cfg), ctypes.byref(h)), "mtv_create")
             eng.handle, eng.device, eng.synced = h, device, False

@@ -26,11 +26,12 @@ DEV = "cuda:0"
 _MODELS = {}
 
 
-def model_for(cfg_name, wseed=0):
-    key = (cfg_name, wseed)
+def model_for(cfg_name, wseed=0, kernel_path=0):
+    key = (cfg_name, wseed, kernel_path)
     if key not in _MODELS:
         cfg = config_by_name(cfg_name)
         m = DiffusionWrapper(UNetModel(**cfg))
+        m.diffusion_model.kernel_path = kernel_path
         m.load_state_dict(synth_state_dict(cfg, wseed, "diffusion_model."), strict=True)
         _MODELS[key] = m.to(DEV).eval()
     return _MODELS[key]
@@ -113,6 +114,31 @@ def test_stagewise_against_oracle_fresh_inputs():
     assert_close(eps, ref, "tiny eps vs oracle")
 
 
+@pytest.mark.parametrize("cfg_name,B", [("tiny", 2), ("base", 1), ("base", 3)])
+def test_tensor_core_path_matches_cuda_core_path(cfg_name, B):
+    """tcgen05 split-bf16 tap-GEMMs vs the fp32 CUDA-core kernels on the same GPU, every
+    stage; the first stage that departs is named (bar 1e-4: the split keeps ~16 mantissa bits)."""
+    cfg = config_by_name(cfg_name)
+    tc, cc = model_for(cfg_name, 0, 0), model_for(cfg_name, 0, 1)
+    x, cond, ic, t = synth_inputs(B, seed=77, t=[(37 * (i + 1)) % 1000 for i in range(B)])
+    e_tc, e_cc = run(tc, x, cond, ic, t), run(cc, x, cond, ic, t)
+    lv = stage_levels(cfg)
+    arch = build_arch(**cfg)
+    order = [f"in{i}" for i in range(len(arch.input_stages))] + ["mid"] + [f"out{i}" for i in range(len(arch.output_stages))]
+    errs = []
+    for k in order:
+        C, L = lv[k]
+        a = tc.diffusion_model.debug_read(k, B, C, L).cpu()
+        b = cc.diffusion_model.debug_read(k, B, C, L).cpu()
+        errs.append((k, rel_l2(a, b), max_abs_rel(a, b)))
+    print(f"{cfg_name} B={B} tc-vs-cuda-core stage errors:", [(k, f"{a:.1e}", f"{m:.1e}") for k, a, m in errs])
+    for k, a, m in errs:
+        assert a <= 1e-4 and m <= 1e-4, f"first departing stage {k}: rel-L2 {a:.3e} max {m:.3e}; all: {errs}"
+    assert_close(e_tc, e_cc, "eps tc vs cuda-core", tol_l2=1e-4, tol_max=1e-4)
+    info = tc.diffusion_model.plan_info(B)
+    assert info["launches"] > 0
+
+
 def test_eager_capture_replay_are_bit_identical():
     model = model_for("tiny", wseed=4)     # fresh handle: 1st call eager, 2nd captures, 3rd+ replays the graph
     x, cond, ic, t = synth_inputs(2, seed=31, t=[10, 700])
@@ -135,7 +161,7 @@ def test_batch_independence_full_config():
     assert bool(torch.isfinite(full).all())
     for b in (0, 3):
         one = run(model, x[b:b + 1], cond[b:b + 1], ic[b:b + 1], t[b:b + 1])
-        assert_close(full[b:b + 1], one, f"sample {b} of batch vs alone", tol_l2=2e-5, tol_max=2e-5)
+        assert_close(full[b:b + 1], one, f"sample {b} of batch vs alone", tol_l2=1e-4, tol_max=1e-4)
 
 
 def test_image_cond_only_xy_plane_is_read():
@@ -205,9 +231,9 @@ def test_ddim_step_and_q_sample_are_bit_exact():
     img, eps, nz = (torch.randn(2, 4, 2048, generator=g) * sc for sc in (1.0, 1.0, 1.0))
     for time, tn in ((999, 989), (509, 499), (19, 9), (9, -1)):
         want = ddim_update(img.clone(), eps, nz, s, time, tn)
-        d_img = img.to(DEV).clone()
+        d_img, d_eps, d_nz = img.to(DEV).clone(), eps.to(DEV), nz.to(DEV)   # keep the device buffers alive
         sr, srm1, san, c, sigma = ddpm.step_scalars(time, tn)
-        rc = lib.mtv_ddim_step(h, d_img.data_ptr(), eps.to(DEV).data_ptr(), nz.to(DEV).data_ptr(), d_img.numel(),
+        rc = lib.mtv_ddim_step(h, d_img.data_ptr(), d_eps.data_ptr(), d_nz.data_ptr(), d_img.numel(),
                                sr, srm1, san, c, sigma, 1 if tn < 0 else 0, None)
         assert rc == 0
         torch.cuda.synchronize()
