@@ -286,10 +286,11 @@ def main():
         fam = {}
         if rank == 0:
             tc = tconds[pairs[0][0]]
+            os.environ["MTV_PROFILE_REPS"] = "10"     # each launch repeated back to back: steady-state per-launch time
             for _ in range(3):
                 _, rows = model.diffusion_model.profile_forward(img, cond, ic, tc)
             acc = {}
-            reps = 5
+            reps = 3
             for _ in range(reps):
                 _, rows = model.diffusion_model.profile_forward(img, cond, ic, tc)
                 for name, us, flops, byts in rows:

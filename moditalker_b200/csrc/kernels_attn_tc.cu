@@ -1,0 +1,398 @@
+// kernels_attn_tc.cu — FlashAttention-style QKVAttentionLegacy on tcgen05 (sm_100a).
+//
+// Reference: QKVAttentionLegacy.forward (MToV/models/ddpm/unet.py:312-326) as used by
+// AttentionBlock (per plane, unet.py:248-254) and AttentionBlock1D (cross-plane,
+// unet.py:295-300): softmax((q s)^T (k s)) v per (sample, head), s = D^-1/4, fp32 softmax.
+//
+//   k_qkv_split : qkv fp32 [B][L][3C] (head-major q|k|v channel order, unet.py:321) ->
+//                 split-bf16 Q (pre-scaled by log2(e)/sqrt(D)), K as [B*H][L][D] and V^T as
+//                 [B*H][D][L], so every MMA operand is K-major and TMA-loadable.
+//   k_attn_tc<D>: one CTA = 128 queries of one (sample, head, segment).  Per 64-key block:
+//                 S = Q K^T            tcgen05.mma, 128x64 fp32 in TMEM (3 split-bf16 MMAs / k-step)
+//                 online softmax       4 warps, thread == query row: tcgen05.ld S, exp2, P -> smem
+//                                      as split bf16 in the UMMA 128B-swizzled K-major layout
+//                 O_blk = P V          tcgen05.mma, 128xD fp32 in TMEM, folded into registers
+//                 The L x L score matrix never exists (reference: 134 MB per top-level call).
+//                 S(j+1) is issued while the softmax of block j runs.
+#include "mtv_kernels.cuh"
+#include "mtv_tc.cuh"
+
+#include <cuda_bf16.h>
+
+namespace mtv {
+
+namespace {
+
+__device__ __forceinline__ uint32_t a_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void a_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void a_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void a_mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void a_mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = a_smem_u32(bar);
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void a_tma_2d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void a_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void a_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major operand descriptor; swizzle span = bytes per row (32 / 64 / 128); 8-row groups are
+// 8*row_bytes apart (SmemDescriptor fields as in kernels_tc.cu; layout codes: 128B=2, 64B=4, 32B=6).
+__device__ __forceinline__ uint64_t a_desc(uint32_t smem_addr, int row_bytes) {
+  const uint64_t layout = row_bytes == 128 ? 2 : (row_bytes == 64 ? 4 : 6);
+  uint64_t d = (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)((8 * row_bytes) >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= layout << 61;
+  return d;
+}
+__host__ __device__ constexpr uint32_t a_idesc(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void a_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void a_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(a_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void a_tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void a_tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void a_tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ qkv -> split operands
+__global__ void __launch_bounds__(128) k_qkv_split(const __grid_constant__ QkvSplitParams P) {
+  const int D = P.C / P.heads;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;     // (b, head, token), token fastest
+  const size_t total = (size_t)P.B * P.heads * P.L;
+  if (idx >= total) return;
+  const int tok = (int)(idx % P.L);
+  const int bh = (int)(idx / P.L);
+  const int b = bh / P.heads, h = bh - b * P.heads;
+  const float* row = P.qkv + ((size_t)b * P.L + tok) * (3 * P.C) + (size_t)h * 3 * D;
+  const float qs = 1.4426950408889634f * rsqrtf((float)D);    // both D^-1/4 factors and log2(e)
+  __nv_bfloat16* Qh = reinterpret_cast<__nv_bfloat16*>(P.q_hi) + ((size_t)bh * P.L + tok) * D;
+  __nv_bfloat16* Ql = reinterpret_cast<__nv_bfloat16*>(P.q_lo) + ((size_t)bh * P.L + tok) * D;
+  __nv_bfloat16* Kh = reinterpret_cast<__nv_bfloat16*>(P.k_hi) + ((size_t)bh * P.L + tok) * D;
+  __nv_bfloat16* Kl = reinterpret_cast<__nv_bfloat16*>(P.k_lo) + ((size_t)bh * P.L + tok) * D;
+  __nv_bfloat16* Vh = reinterpret_cast<__nv_bfloat16*>(P.vt_hi) + (size_t)bh * D * P.L + tok;
+  __nv_bfloat16* Vl = reinterpret_cast<__nv_bfloat16*>(P.vt_lo) + (size_t)bh * D * P.L + tok;
+  for (int d = 0; d < D; d += 4) {
+    const float4 q = __ldg(reinterpret_cast<const float4*>(row + d));
+    const float4 k = __ldg(reinterpret_cast<const float4*>(row + D + d));
+    const float4 v = __ldg(reinterpret_cast<const float4*>(row + 2 * D + d));
+    const float qv[4] = {q.x * qs, q.y * qs, q.z * qs, q.w * qs}, kv[4] = {k.x, k.y, k.z, k.w}, vv[4] = {v.x, v.y, v.z, v.w};
+    __nv_bfloat16 qh[4], ql[4], kh[4], kl[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      qh[i] = __float2bfloat16_rn(qv[i]); ql[i] = __float2bfloat16_rn(qv[i] - __bfloat162float(qh[i]));
+      kh[i] = __float2bfloat16_rn(kv[i]); kl[i] = __float2bfloat16_rn(kv[i] - __bfloat162float(kh[i]));
+      const __nv_bfloat16 vh = __float2bfloat16_rn(vv[i]);
+      Vh[(size_t)(d + i) * P.L] = vh;
+      Vl[(size_t)(d + i) * P.L] = __float2bfloat16_rn(vv[i] - __bfloat162float(vh));
+    }
+    *reinterpret_cast<uint2*>(Qh + d) = *reinterpret_cast<const uint2*>(qh);
+    *reinterpret_cast<uint2*>(Ql + d) = *reinterpret_cast<const uint2*>(ql);
+    *reinterpret_cast<uint2*>(Kh + d) = *reinterpret_cast<const uint2*>(kh);
+    *reinterpret_cast<uint2*>(Kl + d) = *reinterpret_cast<const uint2*>(kl);
+  }
+}
+cudaError_t launch_qkv_split(const QkvSplitParams& P, cudaStream_t s) {
+  const size_t total = (size_t)P.B * P.heads * P.L;
+  k_qkv_split<<<(unsigned)((total + 127) / 128), 128, 0, s>>>(P);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ attention
+constexpr int AT_BQ = 128, AT_BKV = 64, AT_THREADS = 192, AT_NS = 3;
+
+template <int D>
+struct AttnSmem {
+  static constexpr int ROWB = 2 * D;                       // bytes per Q/K row (swizzle span)
+  static constexpr int Q_BYTES = AT_BQ * ROWB;             // one of hi/lo
+  static constexpr int K_BYTES = AT_BKV * ROWB;
+  static constexpr int V_BYTES = D * 128;                  // V^T tile: D rows x 64 keys bf16
+  static constexpr int align_up(int v) { return (v + 1023) & ~1023; }
+  static constexpr int Q_SLOT = align_up(Q_BYTES), K_SLOT = align_up(K_BYTES), V_SLOT = align_up(V_BYTES);
+  static constexpr int STAGE = 2 * K_SLOT + 2 * V_SLOT;
+  static constexpr int P_SLOT = AT_BQ * 128;               // P tile: 128 rows x 64 keys bf16
+  static constexpr int TOTAL = 2 * Q_SLOT + AT_NS * STAGE + 2 * P_SLOT + 1024;
+  static constexpr int STAGE_TX = 2 * K_BYTES + 2 * V_BYTES;
+};
+
+template <int D>
+__global__ void __launch_bounds__(AT_THREADS, 1) k_attn_tc(const __grid_constant__ AttnTcParams P) {
+  using SM = AttnSmem<D>;
+  constexpr uint32_t IDESC_S = a_idesc(AT_BQ, AT_BKV);
+  constexpr uint32_t IDESC_O = a_idesc(AT_BQ, D);
+  constexpr int TMEM_COLS = 128;                           // S: cols [0,64), O block: cols [64, 64+D)
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_q, bar_full[AT_NS], bar_empty[AT_NS], bar_s_full, bar_s_free, bar_p_full, bar_o_full;
+  __shared__ uint32_t tmem_base_s;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t smem0 = (a_smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sQ_hi = smem0, sQ_lo = smem0 + SM::Q_SLOT;
+  const uint32_t sStage0 = smem0 + 2 * SM::Q_SLOT;
+  const uint32_t sP_hi = sStage0 + AT_NS * SM::STAGE, sP_lo = sP_hi + SM::P_SLOT;
+
+  // which (segment, query tile), (sample, head)
+  int sg = 0, qb = blockIdx.x;
+  for (; sg < P.nseg; ++sg) {
+    const int nb = (P.seg_off[sg + 1] - P.seg_off[sg] + AT_BQ - 1) / AT_BQ;
+    if (qb < nb) break;
+    qb -= nb;
+  }
+  const int bh = blockIdx.y;
+  const int t_lo = P.seg_off[sg], len = P.seg_off[sg + 1] - t_lo;
+  const int q0 = qb * AT_BQ;
+  const int nblk = (len + AT_BKV - 1) / AT_BKV;
+
+  if (threadIdx.x == 0) {
+    a_mbar_init(&bar_q, 1);
+    for (int s = 0; s < AT_NS; ++s) { a_mbar_init(&bar_full[s], 1); a_mbar_init(&bar_empty[s], 1); }
+    a_mbar_init(&bar_s_full, 1); a_mbar_init(&bar_o_full, 1);
+    a_mbar_init(&bar_s_free, 128); a_mbar_init(&bar_p_full, 128);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(a_smem_u32(&tmem_base_s)), "r"((uint32_t)TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  a_fence_before();
+  __syncthreads();
+  a_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 64;
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    if (lane == 0) {
+      a_mbar_expect_tx(&bar_q, 2 * SM::Q_BYTES);
+      a_tma_2d(sQ_hi, &P.tmQ_hi, a_smem_u32(&bar_q), 0, bh * P.L + t_lo + q0);
+      a_tma_2d(sQ_lo, &P.tmQ_lo, a_smem_u32(&bar_q), 0, bh * P.L + t_lo + q0);
+      int stage = 0; uint32_t phase = 0;
+      for (int j = 0; j < nblk; ++j) {
+        a_mbar_wait(&bar_empty[stage], phase ^ 1u);
+        a_mbar_expect_tx(&bar_full[stage], SM::STAGE_TX);
+        const uint32_t sK_hi = sStage0 + stage * SM::STAGE, sK_lo = sK_hi + SM::K_SLOT;
+        const uint32_t sV_hi = sK_lo + SM::K_SLOT, sV_lo = sV_hi + SM::V_SLOT;
+        const uint32_t fb = a_smem_u32(&bar_full[stage]);
+        const int krow = bh * P.L + t_lo + j * AT_BKV;
+        a_tma_2d(sK_hi, &P.tmK_hi, fb, 0, krow);
+        a_tma_2d(sK_lo, &P.tmK_lo, fb, 0, krow);
+        a_tma_2d(sV_hi, &P.tmV_hi, fb, t_lo + j * AT_BKV, bh * D);
+        a_tma_2d(sV_lo, &P.tmV_lo, fb, t_lo + j * AT_BKV, bh * D);
+        if (++stage == AT_NS) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer =================================
+    if (lane == 0) {
+      auto issue_S = [&](int stage) {
+        const uint32_t sK_hi = sStage0 + stage * SM::STAGE, sK_lo = sK_hi + SM::K_SLOT;
+#pragma unroll
+        for (int k = 0; k < D / 16; ++k) {
+          const uint64_t qh = a_desc(sQ_hi + k * 32, SM::ROWB), ql = a_desc(sQ_lo + k * 32, SM::ROWB);
+          const uint64_t kh = a_desc(sK_hi + k * 32, SM::ROWB), kl = a_desc(sK_lo + k * 32, SM::ROWB);
+          a_mma(tmem_S, qh, kh, IDESC_S, k > 0 ? 1u : 0u);
+          a_mma(tmem_S, ql, kh, IDESC_S, 1u);
+          a_mma(tmem_S, qh, kl, IDESC_S, 1u);
+        }
+        a_commit(&bar_s_full);
+      };
+      a_mbar_wait(&bar_q, 0);
+      a_mbar_wait(&bar_full[0], 0);
+      a_fence_after();
+      issue_S(0);
+      int stage = 0; uint32_t phase = 0;
+      for (int j = 0; j < nblk; ++j) {
+        int nstage = stage + 1; uint32_t nphase = phase;
+        if (nstage == AT_NS) { nstage = 0; nphase ^= 1u; }
+        if (j + 1 < nblk) {
+          a_mbar_wait(&bar_full[nstage], nphase);
+          a_mbar_wait(&bar_s_free, (uint32_t)(j & 1));      // softmax has read S(j) out of TMEM
+          a_fence_after();
+          issue_S(nstage);
+        }
+        a_mbar_wait(&bar_p_full, (uint32_t)(j & 1));        // P(j) is in smem, O block (j-1) was consumed
+        a_fence_after();
+        const uint32_t sV_hi = sStage0 + stage * SM::STAGE + 2 * SM::K_SLOT, sV_lo = sV_hi + SM::V_SLOT;
+#pragma unroll
+        for (int k = 0; k < AT_BKV / 16; ++k) {
+          const uint64_t ph = a_desc(sP_hi + k * 32, 128), pl = a_desc(sP_lo + k * 32, 128);
+          const uint64_t vh = a_desc(sV_hi + k * 32, 128), vl = a_desc(sV_lo + k * 32, 128);
+          a_mma(tmem_O, ph, vh, IDESC_O, k > 0 ? 1u : 0u);
+          a_mma(tmem_O, pl, vh, IDESC_O, 1u);
+          a_mma(tmem_O, ph, vl, IDESC_O, 1u);
+        }
+        a_commit(&bar_o_full);
+        a_commit(&bar_empty[stage]);
+        stage = nstage; phase = nphase;
+      }
+    }
+  } else {
+    // =============================== softmax / epilogue ==========================
+    const int qq = warp & 3;
+    const int row = qq * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(qq * 32) << 16;
+    float m_run = -INFINITY, l_run = 0.f;
+    float o[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) o[d] = 0.f;
+
+    auto fold_O = [&]() {   // o += O_blk (TMEM cols [64, 64+D))
+#pragma unroll
+      for (int c = 0; c < D; c += 16) {
+        uint32_t r[16];
+        a_tmem_ld16(tmem_O + lane_addr + (uint32_t)c, r);
+        a_tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) o[c + i] += __uint_as_float(r[i]);
+      }
+    };
+
+    for (int j = 0; j < nblk; ++j) {
+      a_mbar_wait(&bar_s_full, (uint32_t)(j & 1));
+      a_fence_after();
+      float s[AT_BKV];
+      {
+        uint32_t r[32];
+        a_tmem_ld32(tmem_S + lane_addr, r);
+        a_tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) s[i] = __uint_as_float(r[i]);
+        a_tmem_ld32(tmem_S + lane_addr + 32u, r);
+        a_tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) s[32 + i] = __uint_as_float(r[i]);
+      }
+      a_fence_before();
+      a_mbar_arrive(&bar_s_free);                           // S TMEM may be overwritten by S(j+1)
+      const int valid = min(AT_BKV, len - j * AT_BKV);
+      float mx = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < AT_BKV; ++i) { if (i >= valid) s[i] = -INFINITY; mx = fmaxf(mx, s[i]); }
+      const float m_new = fmaxf(m_run, mx);
+      const float corr = exp2f(m_run - m_new);
+      float sum = 0.f;
+#pragma unroll
+      for (int i = 0; i < AT_BKV; ++i) { s[i] = exp2f(s[i] - m_new); sum += s[i]; }
+      if (j > 0) {                                          // O block (j-1) finished -> fold it in before rescaling
+        a_mbar_wait(&bar_o_full, (uint32_t)((j - 1) & 1));
+        a_fence_after();
+        fold_O();
+      }
+      l_run = l_run * corr + sum;
+      m_run = m_new;
+#pragma unroll
+      for (int d = 0; d < D; ++d) o[d] *= corr;
+      // P(j) -> smem, split bf16, 128B-swizzled K-major rows (16-byte chunk c of row r at c ^ (r & 7))
+      {
+        const uint32_t rbase_hi = sP_hi + (uint32_t)row * 128u, rbase_lo = sP_lo + (uint32_t)row * 128u;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          uint32_t hi[4], lo[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float p0 = s[c * 8 + 2 * e], p1 = s[c * 8 + 2 * e + 1];
+            const __nv_bfloat16 h0 = __float2bfloat16_rn(p0), h1 = __float2bfloat16_rn(p1);
+            hi[e] = pack_bf16(__bfloat162float(h0), __bfloat162float(h1));
+            lo[e] = pack_bf16(p0 - __bfloat162float(h0), p1 - __bfloat162float(h1));
+          }
+          const uint32_t off = (uint32_t)((c ^ (row & 7)) * 16);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rbase_hi + off), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rbase_lo + off), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA (async proxy)
+      a_fence_before();
+      a_mbar_arrive(&bar_p_full);
+    }
+    a_mbar_wait(&bar_o_full, (uint32_t)((nblk - 1) & 1));
+    a_fence_after();
+    fold_O();
+    const int q = q0 + row;
+    if (q < len) {
+      const int b = bh / P.heads, h = bh - b * P.heads;
+      const float inv = 1.0f / l_run;
+      float* dst = P.out + ((size_t)b * P.L + t_lo + q) * P.C + h * D;
+#pragma unroll
+      for (int d = 0; d < D; d += 4)
+        *reinterpret_cast<float4*>(dst + d) = make_float4(o[d] * inv, o[d + 1] * inv, o[d + 2] * inv, o[d + 3] * inv);
+    }
+  }
+  a_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    a_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+  }
+}
+
+template <int D>
+static cudaError_t launch_attn_tc_d(const AttnTcParams& P, cudaStream_t s) {
+  using SM = AttnSmem<D>;
+  cudaError_t e = cudaFuncSetAttribute(k_attn_tc<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL);
+  if (e != cudaSuccess) return e;
+  int nqb = 0;
+  for (int i = 0; i < P.nseg; ++i) nqb += (P.seg_off[i + 1] - P.seg_off[i] + AT_BQ - 1) / AT_BQ;
+  dim3 grid(nqb, P.B * P.heads);
+  k_attn_tc<D><<<grid, AT_THREADS, SM::TOTAL, s>>>(P);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_attn_tc(const AttnTcParams& P, cudaStream_t s) {
+  switch (P.C / P.heads) {
+    case 16: return launch_attn_tc_d<16>(P, s);
+    case 32: return launch_attn_tc_d<32>(P, s);
+    case 64: return launch_attn_tc_d<64>(P, s);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+}  // namespace mtv

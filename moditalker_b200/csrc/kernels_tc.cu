@@ -88,7 +88,112 @@ __global__ void __launch_bounds__(256) k_apply_split(const __grid_constant__ App
   *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(P.lo) + o) = *reinterpret_cast<const uint2*>(lo);
 }
 
+// GroupNorm32 finalise + apply in ONE kernel: group statistics come from the per-channel sums the
+// producing tap-GEMM accumulated in its epilogue (csum[b][plane][c][2], fp64), so no separate
+// statistics pass reads the activation again.  CTA = (token chunk, plane, sample); prologue turns
+// the sums of that (sample, plane | all planes) into the per-channel affine in shared memory
+// (FiLM folded in), then the body is k_apply_split's.
+__global__ void __launch_bounds__(256) k_apply_norm_split(const __grid_constant__ ApplyParams P) {
+  extern __shared__ float s_aff[];                 // a[C] | d[C]
+  __shared__ double s_mean[32], s_rstd[32];
+  const int C = P.C0 + P.C1, cpg = C / 32;
+  const int p = blockIdx.y, b = blockIdx.z;
+  const Geo g = P.geo;
+  const int plane_tokens = p == 0 ? g.res * g.res : g.t * g.res;
+  const int t0 = blockIdx.x * P.chunk_tokens;
+  if (t0 >= plane_tokens) return;
+  const int t1 = min(plane_tokens, t0 + P.chunk_tokens);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const Geo gs = P.resample == RS_NONE ? g : (P.resample == RS_UP2 ? geo_down(g) : geo_up(g));
+  const double cnt = (double)cpg * (P.joint ? (double)gs.L : (double)(p == 0 ? gs.res * gs.res : gs.t * gs.res));
+  for (int grp = warp; grp < 32; grp += 8) {
+    double s = 0.0, ss = 0.0;
+    for (int ci = lane; ci < cpg; ci += 32) {
+      const int c = grp * cpg + ci;
+      const double* cs; int Cs, cc;
+      if (c < P.C0) { cs = P.csum0; Cs = P.C0; cc = c; } else { cs = P.csum1; Cs = P.C1; cc = c - P.C0; }
+      if (P.joint) {
+#pragma unroll
+        for (int pp = 0; pp < 3; ++pp) { const double* q = cs + (((size_t)b * 3 + pp) * Cs + cc) * 2; s += q[0]; ss += q[1]; }
+      } else {
+        const double* q = cs + (((size_t)b * 3 + p) * Cs + cc) * 2; s += q[0]; ss += q[1];
+      }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, off); ss += __shfl_xor_sync(0xffffffffu, ss, off); }
+    if (lane == 0) {
+      const double mean = s / cnt;
+      double var = ss / cnt - mean * mean; var = var < 0.0 ? 0.0 : var;
+      s_mean[grp] = mean; s_rstd[grp] = rsqrt(var + 1e-5);
+    }
+  }
+  __syncthreads();
+  float* sa = s_aff; float* sd = s_aff + C;
+  for (int c = tid; c < C; c += 256) {
+    const int grp = c / cpg;
+    double a = s_rstd[grp] * (double)__ldg(P.gamma + c);
+    double d = (double)__ldg(P.beta + c) - s_mean[grp] * a;
+    if (P.film) {
+      const float* f = P.film + (size_t)b * P.film_stride;
+      const double sc = 1.0 + (double)__ldg(f + c);
+      a *= sc; d = d * sc + (double)__ldg(f + C + c);
+    }
+    sa[c] = (float)a; sd[c] = (float)d;
+  }
+  __syncthreads();
+  const int cq = C >> 2;
+  const int poff = tc_plane_off(g, p);
+  const int total = (t1 - t0) * cq;
+  for (int idx = tid; idx < total; idx += 256) {
+    const int tl = t0 + idx / cq, c = (idx % cq) * 4;
+    const int y = tl / g.res, x = tl - y * g.res;
+    const int tok = poff + tl;
+    const float* src; int Cs, cc;
+    if (c < P.C0) { src = P.src0; Cs = P.C0; cc = c; } else { src = P.src1; Cs = P.C1; cc = c - P.C0; }
+    const float4 na = *reinterpret_cast<const float4*>(sa + c), nd = *reinterpret_cast<const float4*>(sd + c);
+    auto xf = [&](float4 v) {
+      v.x = fmaf(v.x, na.x, nd.x); v.y = fmaf(v.y, na.y, nd.y); v.z = fmaf(v.z, na.z, nd.z); v.w = fmaf(v.w, na.w, nd.w);
+      if (P.silu) { v.x = silu_tc(v.x); v.y = silu_tc(v.y); v.z = silu_tc(v.z); v.w = silu_tc(v.w); }
+      return v;
+    };
+    float4 v;
+    if (P.resample == RS_NONE) {
+      v = xf(__ldg(reinterpret_cast<const float4*>(src + ((size_t)b * g.L + tok) * Cs + cc)));
+    } else if (P.resample == RS_UP2) {
+      const int ts = tc_plane_off(gs, p) + (y >> 1) * gs.res + (x >> 1);
+      v = xf(__ldg(reinterpret_cast<const float4*>(src + ((size_t)b * gs.L + ts) * Cs + cc)));
+    } else {
+      const int ts = tc_plane_off(gs, p) + (2 * y) * gs.res + 2 * x;
+      const float* q = src + ((size_t)b * gs.L + ts) * Cs + cc;
+      const float4 v0 = xf(__ldg(reinterpret_cast<const float4*>(q)));
+      const float4 v1 = xf(__ldg(reinterpret_cast<const float4*>(q + Cs)));
+      const float4 v2 = xf(__ldg(reinterpret_cast<const float4*>(q + (size_t)gs.res * Cs)));
+      const float4 v3 = xf(__ldg(reinterpret_cast<const float4*>(q + (size_t)(gs.res + 1) * Cs)));
+      v.x = 0.25f * ((v0.x + v1.x) + (v2.x + v3.x)); v.y = 0.25f * ((v0.y + v1.y) + (v2.y + v3.y));
+      v.z = 0.25f * ((v0.z + v1.z) + (v2.z + v3.z)); v.w = 0.25f * ((v0.w + v1.w) + (v2.w + v3.w));
+    }
+    const float f[4] = {v.x, v.y, v.z, v.w};
+    __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      hi[i] = __float2bfloat16_rn(f[i]);
+      lo[i] = __float2bfloat16_rn(f[i] - __bfloat162float(hi[i]));
+    }
+    const size_t o = ((size_t)b * g.L + tok) * C + c;
+    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(P.hi) + o) = *reinterpret_cast<const uint2*>(hi);
+    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(P.lo) + o) = *reinterpret_cast<const uint2*>(lo);
+  }
+}
+
 cudaError_t launch_apply_split(const ApplyParams& P, cudaStream_t s) {
+  if (P.csum0) {
+    const int C = P.C0 + P.C1;
+    const int maxp = P.geo.res * P.geo.res;
+    dim3 grid((maxp + P.chunk_tokens - 1) / P.chunk_tokens, 3, P.B);
+    const size_t smem = (size_t)C * 2 * sizeof(float);
+    k_apply_norm_split<<<grid, 256, smem, s>>>(P);
+    return cudaGetLastError();
+  }
   const size_t total = (size_t)P.B * P.geo.L * ((P.C0 + P.C1) / 4);
   k_apply_split<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(P);
   return cudaGetLastError();
@@ -143,6 +248,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+               ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
@@ -202,6 +311,105 @@ __host__ __device__ constexpr int tc_stage_bytes(int BN) { return 2 * TC_BM * 12
 __host__ __device__ constexpr int tc_stages(int BN) { return BN == 64 ? 4 : 3; }
 __host__ __device__ constexpr int tc_smem_bytes(int BN) { return tc_stages(BN) * tc_stage_bytes(BN) + 1024; }
 
+// Tile geometry.  Levels with >= 128 tokens per sample (L = 2048, 512): a tile is 128
+// consecutive tokens of one plane of one sample.  Small levels (L = 128, 32): a tile is
+// spt = 128/L whole samples, rows ordered plane-major [xy of the spt samples | yt | xt] so each
+// plane is ONE TMA box with a batch extent (out-of-range samples are zero-filled).
+struct TcTile {
+  bool small; int spt; int b0; int tok0;
+  int nxy, npl;
+};
+__device__ __forceinline__ TcTile tc_tile(const Geo& g, int tile) {
+  TcTile t;
+  t.small = g.L <= TC_BM; t.nxy = g.res * g.res; t.npl = g.t * g.res;
+  if (t.small) { t.spt = TC_BM / g.L; t.b0 = tile * t.spt; t.tok0 = 0; }
+  else { const int tps = g.L / TC_BM; t.spt = 1; t.b0 = tile / tps; t.tok0 = (tile - t.b0 * tps) * TC_BM; }
+  return t;
+}
+// tile row -> (sample, token within the sample)
+__device__ __forceinline__ void tc_row_map(const TcTile& t, int row, int& b, int& tok) {
+  if (!t.small) { b = t.b0; tok = t.tok0 + row; return; }
+  const int e1 = t.spt * t.nxy, e2 = e1 + t.spt * t.npl;
+  if (row < e1) { const int s = row / t.nxy; b = t.b0 + s; tok = row - s * t.nxy; }
+  else if (row < e2) { const int r = row - e1; const int s = r / t.npl; b = t.b0 + s; tok = t.nxy + (r - s * t.npl); }
+  else { const int r = row - e2; const int s = r / t.npl; b = t.b0 + s; tok = t.nxy + t.npl + (r - s * t.npl); }
+}
+
+// one 128-row A operand tile (hi and lo) for K-chunk c0 of tap `tap`
+__device__ __forceinline__ void tc_load_A(const Geo& g, const TcTile& t, const CUtensorMap* mh, const CUtensorMap* ml, int taps,
+                                          int tap, int c0, uint32_t sA_hi, uint32_t sA_lo, uint32_t fb) {
+  if (!t.small) {
+    if (taps == 1) {
+      const int row = t.b0 * g.L + t.tok0;
+      tma_load_2d(sA_hi, &mh[0], fb, c0, row);
+      tma_load_2d(sA_lo, &ml[0], fb, c0, row);
+      return;
+    }
+    const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
+    if (t.tok0 < t.nxy) {
+      const int y0 = t.tok0 / g.res;
+      tma_load_4d(sA_hi, &mh[0], fb, c0, dx, y0 + dy, t.b0);
+      tma_load_4d(sA_lo, &ml[0], fb, c0, dx, y0 + dy, t.b0);
+    } else {
+      const int r = t.tok0 - t.nxy;
+      const int pl = r / t.npl, y0 = (r - pl * t.npl) / g.res;
+      tma_load_5d(sA_hi, &mh[1], fb, c0, dx, y0 + dy, pl, t.b0);
+      tma_load_5d(sA_lo, &ml[1], fb, c0, dx, y0 + dy, pl, t.b0);
+    }
+    return;
+  }
+  const uint32_t o1 = (uint32_t)(t.spt * t.nxy) * 128u, o2 = o1 + (uint32_t)(t.spt * t.npl) * 128u;
+  if (taps == 1) {   // (C, L, B) maps: [0] box = (64, nxy, spt), [1] box = (64, npl, spt)
+    tma_load_3d(sA_hi, &mh[0], fb, c0, 0, t.b0);
+    tma_load_3d(sA_lo, &ml[0], fb, c0, 0, t.b0);
+    tma_load_3d(sA_hi + o1, &mh[1], fb, c0, t.nxy, t.b0);
+    tma_load_3d(sA_lo + o1, &ml[1], fb, c0, t.nxy, t.b0);
+    tma_load_3d(sA_hi + o2, &mh[1], fb, c0, t.nxy + t.npl, t.b0);
+    tma_load_3d(sA_lo + o2, &ml[1], fb, c0, t.nxy + t.npl, t.b0);
+  } else {           // [0] (C,W,H,B) box (64,res,res,spt); [1] (C,W,H,2,B) box (64,res,t,1,spt)
+    const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
+    tma_load_4d(sA_hi, &mh[0], fb, c0, dx, dy, t.b0);
+    tma_load_4d(sA_lo, &ml[0], fb, c0, dx, dy, t.b0);
+    tma_load_5d(sA_hi + o1, &mh[1], fb, c0, dx, dy, 0, t.b0);
+    tma_load_5d(sA_lo + o1, &ml[1], fb, c0, dx, dy, 0, t.b0);
+    tma_load_5d(sA_hi + o2, &mh[1], fb, c0, dx, dy, 1, t.b0);
+    tma_load_5d(sA_lo + o2, &ml[1], fb, c0, dx, dy, 1, t.b0);
+  }
+}
+
+
+// Per-channel (sum, sum of squares) of a 32-column chunk over each aligned group of 8 tile rows,
+// accumulated into csum[b][plane][channel][2] (fp64 atomics).  8 rows never straddle a
+// (sample, plane) boundary at any level (plane sizes are multiples of 8 tokens).  Butterfly
+// transpose-reduce: after the three exchange steps lane l holds columns ((l & 7) << 2) + {0..3}.
+__device__ __forceinline__ void tc_csum_chunk(float (&v)[32], bool live, int lane, double* csum_bp /* &csum[b][plane][n] */) {
+  float q[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) { if (!live) v[i] = 0.f; q[i] = v[i] * v[i]; }
+#pragma unroll
+  for (int step = 0; step < 3; ++step) {
+    const int off = 4 >> step, n = 32 >> step, hn = n >> 1;
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      if (i < hn) {
+        const float sv = up ? v[i] : v[i + hn], sq = up ? q[i] : q[i + hn];
+        const float rv = __shfl_xor_sync(0xffffffffu, sv, off), rq = __shfl_xor_sync(0xffffffffu, sq, off);
+        v[i] = (up ? v[i + hn] : v[i]) + rv;
+        q[i] = (up ? q[i + hn] : q[i]) + rq;
+      }
+    }
+  }
+  if (live) {
+    const int cbase = (lane & 7) << 2;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      atomicAdd(csum_bp + 2 * (cbase + i), (double)v[i]);
+      atomicAdd(csum_bp + 2 * (cbase + i) + 1, (double)q[i]);
+    }
+  }
+}
+
 template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant__ TcConvParams P) {
   constexpr int NS = tc_stages(BN);
@@ -216,11 +424,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
 
   const Geo g = P.geo;
   const int n0 = blockIdx.y * BN;
-  // ---- which 128 tokens does this CTA own?
-  const int tile = blockIdx.x;
-  const int tps = g.L / TC_BM;                       // tiles per sample (16, 4, 1)
-  const int b = tile / tps, tl = tile - b * tps;
-  const int tok0 = tl * TC_BM;
+  const TcTile T = tc_tile(g, blockIdx.x);
 
   // K range of this CTA (split-K over the flattened (tap, 64-channel chunk) space)
   const int kch = P.Cin / TC_BK;
@@ -238,8 +442,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     prefetch_tmap(&P.tmA_hi[0]); prefetch_tmap(&P.tmA_lo[0]); prefetch_tmap(&P.tmW_hi); prefetch_tmap(&P.tmW_lo);
-    if (P.taps == 9) { prefetch_tmap(&P.tmA_hi[1]); prefetch_tmap(&P.tmA_lo[1]); }
-    if (P.Cin2) { prefetch_tmap(&P.tmA2_hi); prefetch_tmap(&P.tmA2_lo); prefetch_tmap(&P.tmW2_hi); prefetch_tmap(&P.tmW2_lo); }
   }
   if (warp == 1) {   // TMEM: BN fp32 accumulator columns x 128 lanes
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"((uint32_t)BN) : "memory");
@@ -262,45 +464,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
         const uint32_t fb = smem_u32(&bar_full[stage]);
         if (it >= it_main) {           // second K-segment: 1x1 conv of the skip operand
           const int c2 = (it - it_main) * TC_BK;
-          const int row = b * g.L + tok0;
-          tma_load_2d(sA_hi, &P.tmA2_hi, fb, c2, row);
-          tma_load_2d(sA_lo, &P.tmA2_lo, fb, c2, row);
+          tc_load_A(g, T, P.tmA2_hi, P.tmA2_lo, 1, 0, c2, sA_hi, sA_lo, fb);
           tma_load_2d(sW_hi, &P.tmW2_hi, fb, c2, n0);
           tma_load_2d(sW_lo, &P.tmW2_lo, fb, c2, n0);
-          if (++stage == NS) { stage = 0; phase ^= 1u; }
-          continue;
-        }
-        const int tap = it / kch, kc = it - tap * kch;
-        const int c0 = kc * TC_BK;
-        if (P.taps == 1) {
-          const int row = b * g.L + tok0;
-          tma_load_2d(sA_hi, &P.tmA_hi[0], fb, c0, row);
-          tma_load_2d(sA_lo, &P.tmA_lo[0], fb, c0, row);
         } else {
-          const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
-          const int nxy = g.res * g.res, npl = g.t * g.res;
-          if (g.L == TC_BM) {
-            // level with 128 tokens per sample: the tile is the whole sample = three boxes
-            // (xy: res rows, yt / xt: t rows each), stacked in token order
-            tma_load_4d(sA_hi, &P.tmA_hi[0], fb, c0, dx, dy, b);
-            tma_load_4d(sA_lo, &P.tmA_lo[0], fb, c0, dx, dy, b);
-            tma_load_5d(sA_hi + nxy * 128, &P.tmA_hi[1], fb, c0, dx, dy, 0, b);
-            tma_load_5d(sA_lo + nxy * 128, &P.tmA_lo[1], fb, c0, dx, dy, 0, b);
-            tma_load_5d(sA_hi + (nxy + npl) * 128, &P.tmA_hi[1], fb, c0, dx, dy, 1, b);
-            tma_load_5d(sA_lo + (nxy + npl) * 128, &P.tmA_lo[1], fb, c0, dx, dy, 1, b);
-          } else if (tok0 < nxy) {
-            const int y0 = tok0 / g.res;
-            tma_load_4d(sA_hi, &P.tmA_hi[0], fb, c0, dx, y0 + dy, b);
-            tma_load_4d(sA_lo, &P.tmA_lo[0], fb, c0, dx, y0 + dy, b);
-          } else {
-            const int r = tok0 - nxy;
-            const int pl = r / npl, y0 = (r - pl * npl) / g.res;
-            tma_load_5d(sA_hi, &P.tmA_hi[1], fb, c0, dx, y0 + dy, pl, b);
-            tma_load_5d(sA_lo, &P.tmA_lo[1], fb, c0, dx, y0 + dy, pl, b);
-          }
+          const int tap = it / kch, kc = it - tap * kch;
+          const int c0 = kc * TC_BK;
+          tc_load_A(g, T, P.tmA_hi, P.tmA_lo, P.taps, tap, c0, sA_hi, sA_lo, fb);
+          tma_load_2d(sW_hi, &P.tmW_hi, fb, c0, tap * P.Cout + n0);
+          tma_load_2d(sW_lo, &P.tmW_lo, fb, c0, tap * P.Cout + n0);
         }
-        tma_load_2d(sW_hi, &P.tmW_hi, fb, c0, tap * P.Cout + n0);
-        tma_load_2d(sW_lo, &P.tmW_lo, fb, c0, tap * P.Cout + n0);
         if (++stage == NS) { stage = 0; phase ^= 1u; }
       }
     }
@@ -329,19 +502,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
   } else {
     // =============================== epilogue ===================================
     const int q = warp & 3;                       // TMEM lane quarter this warp may read
-    const int row = q * 32 + lane;                // token within the tile
-    const int tok = tok0 + row;
+    const int row = q * 32 + lane;                // row of the tile
+    int b, tok; tc_row_map(T, row, b, tok);
+    const bool live = b < P.B;
     const size_t m = (size_t)b * g.L + tok;
     mbar_wait(&bar_acc, 0);
     tc_fence_after();
     int p = 0, y = 0, x = 0;
-    if (P.resid && P.resid_mode != RS_NONE) tc_decode_tok(g, tok, p, y, x);
+    if ((P.resid && P.resid_mode != RS_NONE) || P.csum) tc_decode_tok(g, tok, p, y, x);
+    const int pl_stat = p;
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       uint32_t r[32];
+      __syncwarp();
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
       const int n = n0 + c0;
-      if (P.ksplit > 1) {
+      if (!live) {
+        // rows of samples beyond the batch (partial last tile of a small level): nothing to store
+      } else if (P.ksplit > 1) {
         float* dst = P.partial + ((size_t)blockIdx.z * ((size_t)P.B * g.L) + m) * P.Cout + n;
 #pragma unroll
         for (int j = 0; j < 32; j += 4)
@@ -349,6 +527,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
                                                             __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
       } else {
         float* dst = P.out + m * P.Cout + n;
+        float fv[32];
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
           float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
@@ -378,7 +557,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
             }
           }
           *reinterpret_cast<float4*>(dst + j) = v;
+          fv[j] = v.x; fv[j + 1] = v.y; fv[j + 2] = v.z; fv[j + 3] = v.w;
         }
+        if (P.csum) {   // uniform branch: statistics of the tensor just written, for the next GroupNorm
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(fv[j]);
+        }
+      }
+      if (P.csum && P.ksplit <= 1) {
+        float fv[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) fv[j] = __uint_as_float(r[j]);
+        __syncwarp();
+        tc_csum_chunk(fv, live, lane, P.csum + (((size_t)(live ? b : 0) * 3 + pl_stat) * P.Cout + n) * 2);
       }
     }
   }
@@ -390,54 +581,67 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
   }
 }
 
-// split-K epilogue for the tensor-core path (fixed summation order)
-__global__ void k_tc_splitk_epilogue(const __grid_constant__ TcConvParams P) {
+// split-K epilogue for the tensor-core path (fixed summation order).  A CTA owns 32 rows x 32
+// channels: warp w = channel quad, lane = row, so the per-channel statistics reduce with three
+// shuffles over aligned 8-row groups (never straddling a (sample, plane) boundary).
+__global__ void __launch_bounds__(256) k_tc_splitk_epilogue(const __grid_constant__ TcConvParams P) {
   const Geo g = P.geo;
   const size_t M = (size_t)P.B * g.L;
-  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int nq = P.Cout >> 2;
-  if (idx >= M * nq) return;
-  const size_t m = idx / nq; const int n = (int)(idx - m * nq) * 4;
+  const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
+  const size_t m = (size_t)blockIdx.x * 32 + lane;
+  const int n = blockIdx.y * 32 + wq * 4;
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int z = 0; z < P.ksplit; ++z) {
     const float4 v = *reinterpret_cast<const float4*>(P.partial + ((size_t)z * M + m) * P.Cout + n);
     s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
   }
   if (P.bias) { const float4 bv = __ldg(reinterpret_cast<const float4*>(P.bias + n)); s.x += bv.x; s.y += bv.y; s.z += bv.z; s.w += bv.w; }
+  const int b = (int)(m / g.L), tok = (int)(m - (size_t)b * g.L);
+  int p = 0, y = 0, x = 0;
+  tc_decode_tok(g, tok, p, y, x);
   if (P.resid) {
-    const int b = (int)(m / g.L), tok = (int)(m - (size_t)b * g.L);
     if (P.resid_mode == RS_NONE) {
       const float4 rv = __ldg(reinterpret_cast<const float4*>(P.resid + m * P.Cout + n));
       s.x += rv.x; s.y += rv.y; s.z += rv.z; s.w += rv.w;
+    } else if (P.resid_mode == RS_UP2) {
+      const Geo gs = geo_down(g);
+      const int ts = tc_plane_off(gs, p) + (y >> 1) * gs.res + (x >> 1);
+      const float4 rv = __ldg(reinterpret_cast<const float4*>(P.resid + ((size_t)b * gs.L + ts) * P.Cout + n));
+      s.x += rv.x; s.y += rv.y; s.z += rv.z; s.w += rv.w;
     } else {
-      int p, y, x; tc_decode_tok(g, tok, p, y, x);
-      if (P.resid_mode == RS_UP2) {
-        const Geo gs = geo_down(g);
-        const int ts = tc_plane_off(gs, p) + (y >> 1) * gs.res + (x >> 1);
-        const float4 rv = __ldg(reinterpret_cast<const float4*>(P.resid + ((size_t)b * gs.L + ts) * P.Cout + n));
-        s.x += rv.x; s.y += rv.y; s.z += rv.z; s.w += rv.w;
-      } else {
-        const Geo gs = geo_up(g);
-        const int t0 = tc_plane_off(gs, p) + (2 * y) * gs.res + 2 * x;
-        const float* rp = P.resid + ((size_t)b * gs.L + t0) * P.Cout + n;
-        const float4 r0 = __ldg(reinterpret_cast<const float4*>(rp));
-        const float4 r1 = __ldg(reinterpret_cast<const float4*>(rp + P.Cout));
-        const float4 r2 = __ldg(reinterpret_cast<const float4*>(rp + (size_t)gs.res * P.Cout));
-        const float4 r3 = __ldg(reinterpret_cast<const float4*>(rp + (size_t)(gs.res + 1) * P.Cout));
-        s.x += 0.25f * (r0.x + r1.x + r2.x + r3.x); s.y += 0.25f * (r0.y + r1.y + r2.y + r3.y);
-        s.z += 0.25f * (r0.z + r1.z + r2.z + r3.z); s.w += 0.25f * (r0.w + r1.w + r2.w + r3.w);
-      }
+      const Geo gs = geo_up(g);
+      const int t0 = tc_plane_off(gs, p) + (2 * y) * gs.res + 2 * x;
+      const float* rp = P.resid + ((size_t)b * gs.L + t0) * P.Cout + n;
+      const float4 r0 = __ldg(reinterpret_cast<const float4*>(rp));
+      const float4 r1 = __ldg(reinterpret_cast<const float4*>(rp + P.Cout));
+      const float4 r2 = __ldg(reinterpret_cast<const float4*>(rp + (size_t)gs.res * P.Cout));
+      const float4 r3 = __ldg(reinterpret_cast<const float4*>(rp + (size_t)(gs.res + 1) * P.Cout));
+      s.x += 0.25f * (r0.x + r1.x + r2.x + r3.x); s.y += 0.25f * (r0.y + r1.y + r2.y + r3.y);
+      s.z += 0.25f * (r0.z + r1.z + r2.z + r3.z); s.w += 0.25f * (r0.w + r1.w + r2.w + r3.w);
     }
   }
   *reinterpret_cast<float4*>(P.out + m * P.Cout + n) = s;
+  if (P.csum) {
+    float v[4] = {s.x, s.y, s.z, s.w}, q[4] = {s.x * s.x, s.y * s.y, s.z * s.z, s.w * s.w};
+#pragma unroll
+    for (int off = 1; off < 8; off <<= 1)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { v[i] += __shfl_xor_sync(0xffffffffu, v[i], off); q[i] += __shfl_xor_sync(0xffffffffu, q[i], off); }
+    if ((lane & 7) == 0) {
+      double* dst = P.csum + (((size_t)b * 3 + p) * P.Cout + n) * 2;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { atomicAdd(dst + 2 * i, (double)v[i]); atomicAdd(dst + 2 * i + 1, (double)q[i]); }
+    }
+  }
 }
 
 cudaError_t launch_conv_tc(const TcConvParams& P, cudaStream_t s) {
   const int BN = P.bn;
-  if ((BN != 64 && BN != 128) || P.Cout % BN || (P.B * P.geo.L) % TC_BM || P.Cin % TC_BK || P.Cin2 % TC_BK)
-    return cudaErrorInvalidValue;
+  if ((BN != 64 && BN != 128) || P.Cout % BN || P.Cin % TC_BK || P.Cin2 % TC_BK) return cudaErrorInvalidValue;
+  if (P.geo.L > TC_BM ? (P.geo.L % TC_BM != 0) : (TC_BM % P.geo.L != 0)) return cudaErrorInvalidValue;
   const int M = P.B * P.geo.L;
-  dim3 grid(M / TC_BM, P.Cout / BN, P.ksplit > 1 ? P.ksplit : 1);
+  const int tiles = P.geo.L > TC_BM ? M / TC_BM : (P.B + (TC_BM / P.geo.L) - 1) / (TC_BM / P.geo.L);
+  dim3 grid(tiles, P.Cout / BN, P.ksplit > 1 ? P.ksplit : 1);
   cudaError_t e;
   if (BN == 64) {
     e = cudaFuncSetAttribute(k_conv_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(64));
@@ -451,8 +655,8 @@ cudaError_t launch_conv_tc(const TcConvParams& P, cudaStream_t s) {
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   if (P.ksplit > 1) {
-    const size_t tot = (size_t)M * (P.Cout / 4);
-    k_tc_splitk_epilogue<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(P);
+    dim3 rgrid(M / 32, P.Cout / 32);
+    k_tc_splitk_epilogue<<<rgrid, 256, 0, s>>>(P);
     e = cudaGetLastError();
   }
   return e;

@@ -119,7 +119,7 @@ struct Weight {
   void* hi = nullptr; void* lo = nullptr;   // split-bf16 K-major copy [taps][Cout][Cin] for the tcgen05 path
 };
 
-struct Tensor { float* p = nullptr; int C = 0; int level = 0; };
+struct Tensor { float* p = nullptr; int C = 0; int level = 0; double* csum = nullptr; /* [B][3][C][2] per-channel sums, or null */ };
 
 struct RunCtx {
   const float* x = nullptr; const float* cond = nullptr; const float* image_cond = nullptr;
@@ -139,6 +139,7 @@ struct Plan {
   std::map<std::string, Tensor> taps;
   RunCtx ctx;
   cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr; int runs = 0;
+  char* csum_arena = nullptr; size_t csum_cap = 0, csum_used = 0;
   ~Plan() {
     if (exec) cudaGraphExecDestroy(exec);
     if (graph) cudaGraphDestroy(graph);
@@ -159,7 +160,7 @@ struct MtvHandle_t {
   std::map<int, std::unique_ptr<Plan>> plans;
   Plan* last_plan = nullptr;
   int64_t weight_bytes = 0;
-  int tc_mask = 0x3f;
+  int tc_mask = 0x1ff;
   cudaStream_t cap_stream = nullptr;
   cudaStream_t capture_stream() {
     if (!cap_stream) CK(cudaStreamCreateWithFlags(&cap_stream, cudaStreamNonBlocking));
@@ -278,13 +279,17 @@ EncodeTiledFn encode_tiled_fn() {
   return fn;
 }
 // bf16 tensor, innermost dimension contiguous, 128-byte swizzle, zero fill out of bounds
-CUtensorMap make_tmap_bf16(void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box) {
+CUtensorMap make_tmap_bf16(void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
+                           int swizzle_bytes = 128) {
   CUtensorMap m;
   cuuint64_t gd[5]; cuuint64_t gs[4]; cuuint32_t bx[5]; cuuint32_t es[5];
   for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
   for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
   CUresult r = encode_tiled_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, base, gd, gs, bx, es,
-                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                 swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                                      : (swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B),
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) throw MtvError("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
   return m;
@@ -313,16 +318,34 @@ struct Builder {
     else { nseg = 3; off[0] = 0; off[1] = g.res * g.res; off[2] = off[1] + g.t * g.res; off[3] = g.L; }
   }
 
-  NormRef gn(const std::string& name, const Tensor& x0, const Tensor* x1, bool joint,
-             const float* gamma, const float* beta, int film_off) {
+  // GroupNorm requests are recorded lazily: a tensor-core consumer whose sources carry per-channel
+  // sums finalises the statistics inside its apply kernel; everything else materialises the
+  // stand-alone statistics kernel (k_gn_stats) once.
+  struct NormSpec {
+    std::string name; Tensor x0; bool has_x1 = false; Tensor x1; bool joint = false;
+    const float* gamma = nullptr; const float* beta = nullptr; int film_off = -1;
+    NormRef ref; bool done = false;
+  };
+  std::vector<NormSpec> norms;
+
+  int gn(const std::string& name, const Tensor& x0, const Tensor* x1, bool joint,
+         const float* gamma, const float* beta, int film_off) {
+    NormSpec n; n.name = name; n.x0 = x0; n.has_x1 = x1 != nullptr; if (x1) n.x1 = *x1; n.joint = joint;
+    n.gamma = gamma; n.beta = beta; n.film_off = film_off;
+    if ((x0.C + (x1 ? x1->C : 0)) % 32) throw MtvError("GroupNorm32 needs channels % 32 == 0 at " + name);
+    norms.push_back(n);
+    return (int)norms.size() - 1;
+  }
+  NormRef materialize(int id) {
+    NormSpec& n = norms[id];
+    if (n.done) return n.ref;
     GnParams P{};
-    P.src0 = x0.p; P.C0 = x0.C; P.src1 = x1 ? x1->p : nullptr; P.C1 = x1 ? x1->C : 0;
+    P.src0 = n.x0.p; P.C0 = n.x0.C; P.src1 = n.has_x1 ? n.x1.p : nullptr; P.C1 = n.has_x1 ? n.x1.C : 0;
     const int C = P.C0 + P.C1;
-    if (C % 32) throw MtvError("GroupNorm32 needs channels % 32 == 0 at " + name);
-    P.B = B; P.L = geo(x0.level).L;
-    set_segs(x0.level, joint, P.nseg, P.seg_off);
-    P.gamma = gamma; P.beta = beta;
-    if (film_off >= 0) { P.film = film_buf + film_off; P.film_stride = h->arch.J; }
+    P.B = B; P.L = geo(n.x0.level).L;
+    set_segs(n.x0.level, n.joint, P.nseg, P.seg_off);
+    P.gamma = n.gamma; P.beta = n.beta;
+    if (n.film_off >= 0) { P.film = film_buf + n.film_off; P.film_stride = h->arch.J; }
     P.nrm_a = (float*)dalloc((size_t)B * P.nseg * C * sizeof(float));
     P.nrm_d = (float*)dalloc((size_t)B * P.nseg * C * sizeof(float));
     P.sums = (double*)dalloc((size_t)B * P.nseg * 64 * sizeof(double), true);
@@ -331,19 +354,31 @@ struct Builder {
     for (int i = 0; i < P.nseg; ++i) maxlen = std::max(maxlen, P.seg_off[i + 1] - P.seg_off[i]);
     int chunk = maxlen / 32; chunk = chunk < 4 ? 4 : (chunk > 64 ? 64 : chunk);
     P.chunk_tokens = chunk;
-    Op op; op.name = "gn_stats:" + name; op.bytes = (double)B * P.L * C * 4;
+    Op op; op.name = "gn_stats:" + n.name; op.bytes = (double)B * P.L * C * 4;
     op.fn = [P](cudaStream_t s) { return launch_gn_stats(P, s); };
     pl->ops.push_back(op);
-    return NormRef{P.nrm_a, P.nrm_d, P.nseg};
+    n.ref = NormRef{P.nrm_a, P.nrm_d, P.nseg}; n.done = true;
+    return n.ref;
   }
+  double* alloc_csum(int C) {
+    const size_t bytes = (size_t)B * 3 * C * 2 * sizeof(double);
+    if (pl->csum_used + bytes > pl->csum_cap) throw MtvError("internal: csum arena exhausted");
+    double* p = (double*)(pl->csum_arena + pl->csum_used);
+    pl->csum_used += bytes;
+    return p;
+  }
+  bool fuse_gn() const { return h->cfg.kernel_path != 1 && ((h->tc_mask >> 8) & 1); }
 
   // ---- tensor-core lowering -------------------------------------------------------------
   bool tc_ok(const ConvParams& P) const {
     if (h->cfg.kernel_path == 1 || P.out_chmajor) return false;
-    if (P.geo.L % 128 || P.Cout % 64) return false;
+    if (P.Cout % 64) return false;
+    if (P.geo.L > 128 ? (P.geo.L % 128 != 0) : (128 % P.geo.L != 0)) return false;
     {   // debug bisection mask (MTV_TC_MASK): which op classes may use the tensor-core kernel
-      const int level = P.geo.res == h->cfg.image_size ? 0 : (P.geo.res == h->cfg.image_size / 2 ? 1 : 2);
-      int cls = P.nsegs == 2 ? 4 : (P.seg[0].taps == 1 ? 3 : level);
+      int level = 0;
+      while ((h->cfg.image_size >> level) > P.geo.res) ++level;
+      if (level >= 3 && !((h->tc_mask >> 7) & 1)) return false;          // bit 7: levels with < 128 tokens per sample
+      int cls = P.nsegs == 2 ? 4 : (P.seg[0].taps == 1 ? 3 : (level > 2 ? 2 : level));
       if (!((h->tc_mask >> cls) & 1)) return false;
     }
     for (int s = 0; s < P.nsegs; ++s) {
@@ -355,52 +390,73 @@ struct Builder {
     return true;
   }
   // split-bf16 operand of one K-segment + its TMA maps
-  void tc_operand(const std::string& name, const KSeg& S, const Geo& g, CUtensorMap* a_hi, CUtensorMap* a_lo) {
+  void tc_operand(const std::string& name, const KSeg& S, const Geo& g, CUtensorMap* a_hi, CUtensorMap* a_lo, int norm_id) {
     const int C = S.C0 + S.C1;
     const size_t bytes = (size_t)B * g.L * C * 2;
     void* hi = dalloc(bytes); void* lo = dalloc(bytes);
     ApplyParams A{};
-    A.src0 = S.src0; A.src1 = S.src1; A.C0 = S.C0; A.C1 = S.C1; A.nrm_a = S.nrm_a; A.nrm_d = S.nrm_d; A.nrm_nseg = S.nrm_nseg;
+    A.src0 = S.src0; A.src1 = S.src1; A.C0 = S.C0; A.C1 = S.C1;
     A.silu = S.silu; A.resample = S.resample; A.B = B; A.geo = g; A.hi = hi; A.lo = lo;
+    if (norm_id >= 0) {
+      const NormSpec& n = norms[norm_id];
+      if (fuse_gn() && n.x0.csum && (!n.has_x1 || n.x1.csum)) {
+        A.csum0 = n.x0.csum; A.csum1 = n.has_x1 ? n.x1.csum : nullptr;
+        A.gamma = n.gamma; A.beta = n.beta; A.joint = n.joint ? 1 : 0;
+        if (n.film_off >= 0) { A.film = film_buf + n.film_off; A.film_stride = h->arch.J; }
+        A.chunk_tokens = g.res * g.res >= 256 ? 16 : 8;
+      } else {
+        const NormRef r = materialize(norm_id);
+        A.nrm_a = r.a; A.nrm_d = r.d; A.nrm_nseg = r.nseg;
+      }
+    }
     Op op; op.name = "apply:" + name; op.bytes = (double)B * g.L * C * 8;
     op.fn = [A](cudaStream_t s) { return launch_apply_split(A, s); };
     pl->ops.push_back(op);
     void* ptr[2] = {hi, lo}; CUtensorMap* dst[2] = {a_hi, a_lo};
+    const bool small = g.L <= 128;
+    const uint32_t spt = small ? (uint32_t)(128 / g.L) : 1u;          // samples per tile (kernels_tc.cu: tc_tile)
+    const uint64_t rowb = (uint64_t)C * 2;
     for (int k = 0; k < 2; ++k) {
       char* base = (char*)ptr[k];
-      if (S.taps == 1) {
-        const uint64_t dims[2] = {(uint64_t)C, (uint64_t)B * g.L}; const uint64_t str[1] = {(uint64_t)C * 2};
+      if (S.taps == 1 && !small) {
+        const uint64_t dims[2] = {(uint64_t)C, (uint64_t)B * g.L}; const uint64_t str[1] = {rowb};
         const uint32_t box[2] = {64, 128};
         dst[k][0] = make_tmap_bf16(base, 2, dims, str, box);
+      } else if (S.taps == 1) {
+        const uint64_t dims[3] = {(uint64_t)C, (uint64_t)g.L, (uint64_t)B}; const uint64_t str[2] = {rowb, rowb * g.L};
+        const uint32_t box0[3] = {64, (uint32_t)(g.res * g.res), spt}, box1[3] = {64, (uint32_t)(g.t * g.res), spt};
+        dst[k][0] = make_tmap_bf16(base, 3, dims, str, box0);
+        dst[k][1] = make_tmap_bf16(base, 3, dims, str, box1);
       } else {
-        const uint64_t rowb = (uint64_t)C * 2;
-        const uint32_t hb_xy = g.L == 128 ? (uint32_t)g.res : (uint32_t)(128 / g.res);
-        const uint32_t hb_pl = g.L == 128 ? (uint32_t)g.t : (uint32_t)(128 / g.res);
+        const uint32_t hb_xy = small ? (uint32_t)g.res : (uint32_t)(128 / g.res);
+        const uint32_t hb_pl = small ? (uint32_t)g.t : (uint32_t)(128 / g.res);
         {
           const uint64_t dims[4] = {(uint64_t)C, (uint64_t)g.res, (uint64_t)g.res, (uint64_t)B};
           const uint64_t str[3] = {rowb, rowb * g.res, rowb * g.L};
-          const uint32_t box[4] = {64, (uint32_t)g.res, hb_xy, 1};
+          const uint32_t box[4] = {64, (uint32_t)g.res, hb_xy, spt};
           dst[k][0] = make_tmap_bf16(base, 4, dims, str, box);
         }
         {
           const uint64_t dims[5] = {(uint64_t)C, (uint64_t)g.res, (uint64_t)g.t, 2, (uint64_t)B};
           const uint64_t str[4] = {rowb, rowb * g.res, rowb * g.res * g.t, rowb * g.L};
-          const uint32_t box[5] = {64, (uint32_t)g.res, hb_pl, 1, 1};
+          const uint32_t box[5] = {64, (uint32_t)g.res, hb_pl, 1, spt};
           dst[k][1] = make_tmap_bf16(base + rowb * g.res * g.res, 5, dims, str, box);
         }
       }
     }
   }
-  void conv_tc(const std::string& name, const ConvParams& P) {
+  void conv_tc(const std::string& name, const ConvParams& P, int norm0, int norm1, Tensor* out_t) {
     TcConvParams T{};
+    if (out_t && fuse_gn()) { out_t->csum = alloc_csum(P.Cout); T.csum = out_t->csum; }
     const KSeg& S = P.seg[0];
     T.taps = S.taps; T.Cin = S.C0 + S.C1; T.Cout = P.Cout; T.B = B; T.geo = P.geo;
     T.bias = P.bias; T.resid = P.resid; T.resid_mode = P.resid_mode; T.out = P.out;
     const int M = B * P.geo.L;
+    const int mtiles = P.geo.L > 128 ? M / 128 : (B + (128 / P.geo.L) - 1) / (128 / P.geo.L);
     int bn = 64;
-    if (P.Cout % 128 == 0 && (M / 128) * (P.Cout / 128) >= h->num_sms) bn = 128;
+    if (P.Cout % 128 == 0 && mtiles * (P.Cout / 128) >= h->num_sms) bn = 128;
     T.bn = bn;
-    tc_operand(name, S, P.geo, T.tmA_hi, T.tmA_lo);
+    tc_operand(name, S, P.geo, T.tmA_hi, T.tmA_lo, norm0);
     auto wmaps = [&](const KSeg& K, CUtensorMap& whi, CUtensorMap& wlo) {
       const auto& pr = h->tc_w.at(K.w);
       const int C = K.C0 + K.C1;
@@ -414,16 +470,16 @@ struct Builder {
     if (P.nsegs == 2) {
       const KSeg& X = P.seg[1];
       T.Cin2 = X.C0 + X.C1;
-      tc_operand(name + ".skip", X, P.geo, &T.tmA2_hi, &T.tmA2_lo);
+      tc_operand(name + ".skip", X, P.geo, T.tmA2_hi, T.tmA2_lo, norm1);
       wmaps(X, T.tmW2_hi, T.tmW2_lo);
       Ktot += T.Cin2;
     }
     const int iters = T.taps * (T.Cin / 64) + T.Cin2 / 64;
-    const int base = (M / 128) * (P.Cout / bn);
+    const int base = mtiles * (P.Cout / bn);
     int ks = 1;
     if (base < 64 && iters >= 32 && ((h->tc_mask >> 5) & 1)) {
-      ks = std::min(iters / 8, (128 + base - 1) / base);
-      ks = std::min(ks, 16);
+      ks = std::min(iters / 4, (h->num_sms + base - 1) / base);
+      ks = std::min(ks, 32);
       while (ks > 1 && (ks - 1) * ((iters + ks - 1) / ks) >= iters) --ks;
     }
     T.ksplit = ks;
@@ -435,9 +491,16 @@ struct Builder {
     pl->ops.push_back(op);
   }
 
-  void conv(const std::string& name, ConvParams P, int phase = 1, bool out_is_ctx = false) {
+  void conv(const std::string& name, ConvParams P, int norm0 = -1, int norm1 = -1, Tensor* out_t = nullptr,
+            int phase = 1, bool out_is_ctx = false) {
     P.B = B;
-    if (phase == 1 && !out_is_ctx && tc_ok(P)) { conv_tc(name, P); return; }
+    if (phase == 1 && !out_is_ctx && tc_ok(P)) { conv_tc(name, P, norm0, norm1, out_t); return; }
+    const int nid[2] = {norm0, norm1};
+    for (int s = 0; s < P.nsegs; ++s)
+      if (nid[s] >= 0) {
+        const NormRef r = materialize(nid[s]);
+        P.seg[s].nrm_a = r.a; P.seg[s].nrm_d = r.d; P.seg[s].nrm_nseg = r.nseg;
+      }
     double K = 0;
     for (int s = 0; s < P.nsegs; ++s) {
       const int Ct = P.seg[s].C0 + P.seg[s].C1;
@@ -463,24 +526,24 @@ struct Builder {
     const std::string& p = r.name;
     const int cin = x0.C + (x1 ? x1->C : 0);
     if (cin != r.cin) throw MtvError("internal: channel mismatch at " + p);
-    NormRef n1 = gn(p + ".in_layers.0", x0, x1, false, h->W(p + ".in_layers.0.weight"), h->W(p + ".in_layers.0.bias"), -1);
+    const int n1 = gn(p + ".in_layers.0", x0, x1, false, h->W(p + ".in_layers.0.weight"), h->W(p + ".in_layers.0.bias"), -1);
     Tensor hmid = T(r.cout, level_out);
     {
       ConvParams P{}; P.nsegs = 1; P.geo = geo(level_out); P.Cout = r.cout;
       KSeg& S = P.seg[0];
       S.src0 = x0.p; S.C0 = x0.C; S.src1 = x1 ? x1->p : nullptr; S.C1 = x1 ? x1->C : 0;
-      S.nrm_a = n1.a; S.nrm_d = n1.d; S.nrm_nseg = 3; S.silu = 1; S.resample = r.updown; S.taps = 9;
+      S.silu = 1; S.resample = r.updown; S.taps = 9;
       S.w = h->W(p + ".in_layers.2.weight");
       P.bias = h->W(p + ".in_layers.2.bias"); P.out = hmid.p;
-      conv(p + ".in_layers.2", P);
+      conv(p + ".in_layers.2", P, n1, -1, &hmid);
     }
-    NormRef n2 = gn(p + ".out_layers.0", hmid, nullptr, false, h->W(p + ".out_layers.0.weight"),
-                    h->W(p + ".out_layers.0.bias"), r.film_off);
+    const int n2 = gn(p + ".out_layers.0", hmid, nullptr, false, h->W(p + ".out_layers.0.weight"),
+                      h->W(p + ".out_layers.0.bias"), r.film_off);
     Tensor out = T(r.cout, level_out);
     {
       ConvParams P{}; P.nsegs = 1; P.geo = geo(level_out); P.Cout = r.cout;
       KSeg& S = P.seg[0];
-      S.src0 = hmid.p; S.C0 = r.cout; S.nrm_a = n2.a; S.nrm_d = n2.d; S.nrm_nseg = 3; S.silu = 1;
+      S.src0 = hmid.p; S.C0 = r.cout; S.silu = 1;
       S.resample = RS_NONE; S.taps = 9; S.w = h->W(p + ".out_layers.3.weight");
       if (r.cin != r.cout) {   // 1x1 skip conv folded in as a second K-segment (unet.py:167, 207)
         P.nsegs = 2; KSeg& K1 = P.seg[1];
@@ -493,7 +556,7 @@ struct Builder {
         P.resid = x0.p; P.resid_mode = r.updown;
       }
       P.out = out.p;
-      conv(p + ".out_layers.3", P);
+      conv(p + ".out_layers.3", P, n2, -1, &out);
     }
     return out;
   }
@@ -502,14 +565,14 @@ struct Builder {
     const std::string& p = a.name;
     const int C = a.C, heads = h->cfg.num_heads;
     if (x.C != C) throw MtvError("internal: channel mismatch at " + p);
-    NormRef n = gn(p + ".norm", x, nullptr, a.joint, h->W(p + ".norm.weight"), h->W(p + ".norm.bias"), -1);
+    const int n = gn(p + ".norm", x, nullptr, a.joint, h->W(p + ".norm.weight"), h->W(p + ".norm.bias"), -1);
     Tensor qkv = T(3 * C, level);
     {
       ConvParams P{}; P.nsegs = 1; P.geo = geo(level); P.Cout = 3 * C;
       KSeg& S = P.seg[0];
-      S.src0 = x.p; S.C0 = C; S.nrm_a = n.a; S.nrm_d = n.d; S.nrm_nseg = n.nseg; S.silu = 0; S.taps = 1;
+      S.src0 = x.p; S.C0 = C; S.silu = 0; S.taps = 1;
       S.w = h->W(p + ".qkv.weight"); P.bias = h->W(p + ".qkv.bias"); P.out = qkv.p;
-      conv(p + ".qkv", P);
+      conv(p + ".qkv", P, n);
     }
     Tensor att = T(C, level);
     {
@@ -518,13 +581,41 @@ struct Builder {
       const int D = C / heads;
       if (C % heads || !(D == 16 || D == 32 || D == 64 || D == 128))
         throw MtvError("attention head dim must be 16/32/64/128 at " + p);
-      Op op; op.name = "attn:" + p;
       double pairs = 0;
       for (int i = 0; i < P.nseg; ++i) { const double l = P.seg_off[i + 1] - P.seg_off[i]; pairs += l * l; }
-      op.flops = 4.0 * B * heads * pairs * D;
-      op.bytes = 4.0 * B * P.L * 4 * C;
-      op.fn = [P](cudaStream_t s) { return launch_attn_simt(P, s); };
-      pl->ops.push_back(op);
+      const bool tc_attn = h->cfg.kernel_path != 1 && ((h->tc_mask >> 6) & 1) && (D == 16 || D == 32 || D == 64);
+      if (tc_attn) {
+        const size_t bytes = (size_t)B * P.L * C * 2;
+        QkvSplitParams Q{}; Q.qkv = qkv.p; Q.B = B; Q.L = P.L; Q.C = C; Q.heads = heads;
+        Q.q_hi = dalloc(bytes); Q.q_lo = dalloc(bytes); Q.k_hi = dalloc(bytes); Q.k_lo = dalloc(bytes);
+        Q.vt_hi = dalloc(bytes); Q.vt_lo = dalloc(bytes);
+        { Op op; op.name = "qkv_split:" + p; op.bytes = (double)B * P.L * C * 24;
+          op.fn = [Q](cudaStream_t s) { return launch_qkv_split(Q, s); }; pl->ops.push_back(op); }
+        AttnTcParams T{}; T.out = att.p; T.B = B; T.L = P.L; T.C = C; T.heads = heads; T.nseg = P.nseg;
+        for (int i = 0; i < 4; ++i) T.seg_off[i] = P.seg_off[i];
+        const uint64_t rows = (uint64_t)B * heads * P.L;
+        {
+          const uint64_t dims[2] = {(uint64_t)D, rows}; const uint64_t str[1] = {(uint64_t)D * 2};
+          const uint32_t bq[2] = {(uint32_t)D, 128}, bk[2] = {(uint32_t)D, 64};
+          T.tmQ_hi = make_tmap_bf16(Q.q_hi, 2, dims, str, bq, 2 * D); T.tmQ_lo = make_tmap_bf16(Q.q_lo, 2, dims, str, bq, 2 * D);
+          T.tmK_hi = make_tmap_bf16(Q.k_hi, 2, dims, str, bk, 2 * D); T.tmK_lo = make_tmap_bf16(Q.k_lo, 2, dims, str, bk, 2 * D);
+        }
+        {
+          const uint64_t dims[2] = {(uint64_t)P.L, (uint64_t)B * heads * D}; const uint64_t str[1] = {(uint64_t)P.L * 2};
+          const uint32_t bv[2] = {64, (uint32_t)D};
+          T.tmV_hi = make_tmap_bf16(Q.vt_hi, 2, dims, str, bv, 128); T.tmV_lo = make_tmap_bf16(Q.vt_lo, 2, dims, str, bv, 128);
+        }
+        Op op; op.name = "attn_tc:" + p;
+        op.flops = 4.0 * B * heads * pairs * D; op.bytes = 4.0 * B * P.L * 4 * C;
+        op.fn = [T](cudaStream_t s) { return launch_attn_tc(T, s); };
+        pl->ops.push_back(op);
+      } else {
+        Op op; op.name = "attn:" + p;
+        op.flops = 4.0 * B * heads * pairs * D;
+        op.bytes = 4.0 * B * P.L * 4 * C;
+        op.fn = [P](cudaStream_t s) { return launch_attn_simt(P, s); };
+        pl->ops.push_back(op);
+      }
     }
     Tensor out = T(C, level);
     {
@@ -532,7 +623,7 @@ struct Builder {
       KSeg& S = P.seg[0];
       S.src0 = att.p; S.C0 = C; S.taps = 1; S.w = h->W(p + ".proj_out.weight");
       P.bias = h->W(p + ".proj_out.bias"); P.resid = x.p; P.resid_mode = RS_NONE; P.out = out.p;
-      conv(p + ".proj_out", P);
+      conv(p + ".proj_out", P, -1, -1, &out);
     }
     return out;
   }
@@ -579,6 +670,16 @@ struct Builder {
       pl->ops.push_back(op);
     }
     // ---- timestep embedding + every ResBlock's FiLM scale/shift
+    // per-channel statistics arena (zeroed at the start of every forward, inside the graph)
+    pl->csum_cap = (size_t)B * (8u << 20);
+    pl->csum_arena = (char*)dalloc(pl->csum_cap, true);
+    {
+      Op op; op.name = "zero_csum"; op.launches = 1;
+      op.fn = [plan](cudaStream_t s) {
+        return plan->csum_used ? cudaMemsetAsync(plan->csum_arena, 0, plan->csum_used, s) : cudaSuccess;
+      };
+      pl->ops.push_back(op);
+    }
     film_buf = (float*)dalloc((size_t)B * A.J * sizeof(float));
     {
       EmbParams P{}; P.t = t_buf; P.B = B; P.mc = mc; P.ted = ted; P.freqs = h->freqs;
@@ -603,7 +704,7 @@ struct Builder {
       ConvParams P{}; P.nsegs = 1; P.geo = geo(0); P.Cout = mc;
       KSeg& S = P.seg[0]; S.src0 = xin.p; S.C0 = xin.C; S.taps = 9; S.w = h->W("input_blocks.0.0.weight");
       P.bias = h->W("input_blocks.0.0.bias"); P.out = cur.p;
-      conv("input_blocks.0.0", P);
+      conv("input_blocks.0.0", P, -1, -1, &cur);
       pl->taps["in0"] = cur; skips.push_back(cur);
     }
     for (size_t i = 1; i < A.in.size(); ++i) {
@@ -621,14 +722,14 @@ struct Builder {
       pl->taps["out" + std::to_string(i)] = cur;
     }
     // ---- head: GN -> SiLU -> conv3x3 -> channel-major eps (unet.py:971-975, 1103-1112)
-    NormRef nh = gn("out.0", cur, nullptr, false, h->W("out.0.weight"), h->W("out.0.bias"), -1);
+    const int nh = gn("out.0", cur, nullptr, false, h->W("out.0.weight"), h->W("out.0.bias"), -1);
     float* eps_buf = (float*)dalloc((size_t)B * c.out_channels * geo(0).L * sizeof(float));
     {
       ConvParams P{}; P.nsegs = 1; P.geo = geo(0); P.Cout = c.out_channels;
-      KSeg& S = P.seg[0]; S.src0 = cur.p; S.C0 = cur.C; S.nrm_a = nh.a; S.nrm_d = nh.d; S.nrm_nseg = 3; S.silu = 1;
+      KSeg& S = P.seg[0]; S.src0 = cur.p; S.C0 = cur.C; S.silu = 1;
       S.taps = 9; S.w = h->W("out.2.weight");
       P.bias = h->W("out.2.bias"); P.out = eps_buf; P.out_chmajor = 1;
-      conv("out.2", P);
+      conv("out.2", P, nh);
     }
     {
       Op op; op.name = "copy_out"; op.phase = 2; op.launches = 0;
@@ -872,14 +973,21 @@ int mtv_profile_forward(MtvHandle h, const float* x, const float* cond, const fl
     pl->ctx.x = x; pl->ctx.cond = cond; pl->ctx.image_cond = image_cond; pl->ctx.ic_len = image_cond_len;
     pl->ctx.t = t; pl->ctx.out = out;
     cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    // each op is launched `reps` times back to back between the two events (ops are idempotent):
+    // the per-launch average then carries the steady-state launch gap, not the event overhead
+    int reps = 1;
+    if (const char* rp = getenv("MTV_PROFILE_REPS")) reps = std::max(1, atoi(rp));
     int k = 0;
     for (Op& op : pl->ops) {
       CK(cudaEventRecord(e0, s));
-      cudaError_t e = op.fn(s);
-      if (e != cudaSuccess) throw MtvError("launch failed at " + op.name + ": " + cudaGetErrorString(e));
+      for (int r = 0; r < reps; ++r) {
+        cudaError_t e = op.fn(s);
+        if (e != cudaSuccess) throw MtvError("launch failed at " + op.name + ": " + cudaGetErrorString(e));
+      }
       CK(cudaEventRecord(e1, s));
       CK(cudaEventSynchronize(e1));
       float ms = 0; CK(cudaEventElapsedTime(&ms, e0, e1));
+      ms /= (float)reps;
       if (k < cap) {
         MtvKernelTime& kt = entries[k];
         snprintf(kt.name, sizeof(kt.name), "%s", op.name.c_str());

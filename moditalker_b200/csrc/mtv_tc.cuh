@@ -11,23 +11,50 @@ struct ApplyParams {
   const float* src0; const float* src1; int C0, C1;   // sources at the SOURCE geometry (see resample)
   const float* nrm_a; const float* nrm_d; int nrm_nseg;
   int silu; int resample;                              // RS_*: source geometry relative to `geo`
+  // fused-GroupNorm mode (csum0 != nullptr): statistics come from the producers' per-channel sums
+  const double* csum0; const double* csum1;            // [B][3][C0|C1][2]
+  const float* gamma; const float* beta;               // [C0+C1]
+  const float* film; int film_stride;                  // FiLM row b = film + b*stride: scale[C] | shift[C]; nullptr: none
+  int joint;                                           // statistics over all three planes (AttentionBlock1D.norm)
+  int chunk_tokens;                                    // tokens of one plane per CTA
   int B; Geo geo;                                      // OUTPUT geometry
   void* hi; void* lo;                                  // __nv_bfloat16 [B][L][C0+C1]
 };
 
 // D[B*L][Cout] = sum_tap A_tap[B*L][Cin] * W[tap][Cout][Cin]^T   (+bias, +residual)
 struct TcConvParams {
-  CUtensorMap tmA_hi[2], tmA_lo[2];   // taps==9: [0] xy plane (C,W,H,B), [1] yt|xt planes (C,W,H,2,B); taps==1: [0] = (C, B*L)
+  // L > 128 : taps==9: [0] xy plane (C,W,H,B), [1] yt|xt planes (C,W,H,2,B), 128-token boxes; taps==1: [0] = (C, B*L)
+  // L <= 128: whole-plane boxes with a batch extent of 128/L samples (see tc_tile):
+  //           taps==9: [0] (C,W,H,B), [1] (C,W,H,2,B); taps==1: [0],[1] = (C, L, B) with xy- / plane-sized boxes
+  CUtensorMap tmA_hi[2], tmA_lo[2];
   CUtensorMap tmW_hi, tmW_lo;         // (Cin, taps*Cout), box (64, BN)
   // optional second K-segment: a 1x1 conv of another activation accumulated into the same tile
   // (the ResBlock skip_connection, unet.py:167,207); Cin2 == 0 when absent
-  CUtensorMap tmA2_hi, tmA2_lo;       // (Cin2, B*L)
+  CUtensorMap tmA2_hi[2], tmA2_lo[2]; // like tmA_* with taps == 1
   CUtensorMap tmW2_hi, tmW2_lo;       // (Cin2, Cout)
   int Cin2; int bn;
   int taps, Cin, Cout, B; Geo geo;
   const float* bias; const float* resid; int resid_mode;
   float* out; float* partial; int ksplit;
+  double* csum;                       // optional [B][3][Cout][2]: per-channel sums of `out` for the next GroupNorm
 };
+
+// qkv fp32 [B][L][3C] -> split-bf16 Q (pre-scaled), K [B*H][L][D] and V^T [B*H][D][L]
+struct QkvSplitParams {
+  const float* qkv; int B, L, C, heads;
+  void* q_hi; void* q_lo; void* k_hi; void* k_lo; void* vt_hi; void* vt_lo;
+};
+// softmax(Q K^T) V per (sample, head, segment) on tcgen05
+struct AttnTcParams {
+  CUtensorMap tmQ_hi, tmQ_lo;     // (D, B*H*L) box (D, 128)
+  CUtensorMap tmK_hi, tmK_lo;     // (D, B*H*L) box (D, 64)
+  CUtensorMap tmV_hi, tmV_lo;     // (L, B*H*D) box (64, D)
+  float* out;                     // [B][L][C]
+  int B, L, C, heads;
+  int nseg; int seg_off[4];
+};
+cudaError_t launch_qkv_split(const QkvSplitParams& P, cudaStream_t s);
+cudaError_t launch_attn_tc(const AttnTcParams& P, cudaStream_t s);
 
 cudaError_t launch_apply_split(const ApplyParams& P, cudaStream_t s);
 cudaError_t launch_repack_split_w(const float* src, void* hi, void* lo, int Cout, int Cin, int taps, cudaStream_t s);
