@@ -110,6 +110,11 @@ int  mtv_plan_info(MtvHandle h, int32_t B, int64_t* n_launches, int64_t* workspa
  * as channel-major [B, C, L] fp32.  dst_elems guards the size. */
 int  mtv_debug_read(MtvHandle h, const char* tag, float* dst, int64_t dst_elems, void* stream);
 
+/* Diagnostics: arm (records != NULL) or disarm (NULL) in-kernel phase timing of the tensor-core
+ * tap-GEMM.  While armed every CTA appends one 16 x int64 record to the DEVICE buffer `records`
+ * (capacity `cap` records).  *count receives the number of records written since the previous call. */
+int  mtv_debug_tc_timing(MtvHandle h, int64_t* records, int32_t cap, int32_t* count);
+
 /* Per-kernel timing of one forward (CUDA events around every launch, serialised):
  * fills up to `cap` entries of (name, microseconds); returns the count in *n. */
 typedef struct MtvKernelTime { char name[48]; float us; float flops; float bytes; } MtvKernelTime;

@@ -305,6 +305,22 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// ------------------------------------------------------------------ optional in-kernel timing (diagnostics)
+// When armed through mtv_debug_tc_timing(), every k_conv_tc CTA appends one 16-word record of
+// clock64() stamps of its pipeline phases; scripts/tc_timing.py turns them into a breakdown.
+__device__ long long* g_tc_dbg = nullptr;
+__device__ unsigned int g_tc_dbg_cap = 0;
+__device__ unsigned int g_tc_dbg_count = 0;
+cudaError_t tc_debug_arm(long long* buf, unsigned int cap) {
+  unsigned int zero = 0;
+  cudaError_t e = cudaMemcpyToSymbol(g_tc_dbg, &buf, sizeof(buf));
+  if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_tc_dbg_cap, &cap, sizeof(cap));
+  if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_tc_dbg_count, &zero, sizeof(zero));
+  return e;
+}
+cudaError_t tc_debug_count(unsigned int* n) { return cudaMemcpyFromSymbol(n, g_tc_dbg_count, sizeof(*n)); }
+__device__ __forceinline__ long long gtime_ns() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+
 // ------------------------------------------------------------------ the tap-GEMM
 constexpr int TC_BM = 128, TC_BK = 64, TC_THREADS = 192;
 __host__ __device__ constexpr int tc_stage_bytes(int BN) { return 2 * TC_BM * 128 + 2 * BN * 128; }
@@ -418,6 +434,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_full[NS], bar_empty[NS], bar_acc;
   __shared__ uint32_t tmem_base_s;
+  __shared__ long long s_stamp[8];
+  const bool dbg = g_tc_dbg != nullptr;
+  long long g_t0 = 0;
+  if (dbg && threadIdx.x == 0) { s_stamp[0] = clock64(); g_t0 = gtime_ns(); }
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B tiles need 1024-B alignment
@@ -451,6 +471,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
+  if (dbg && threadIdx.x == 0) s_stamp[1] = clock64();
 
   if (warp == 0) {
     // =============================== TMA producer ===============================
@@ -458,6 +479,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
       int stage = 0; uint32_t phase = 0;
       for (int it = it0; it < it1; ++it) {
         mbar_wait(&bar_empty[stage], phase ^ 1u);
+        if (dbg && it == it1 - 1) s_stamp[2] = clock64();          // last stage request issued
         mbar_expect_tx(&bar_full[stage], (uint32_t)STAGE);
         const uint32_t sA_hi = smem0 + stage * STAGE, sA_lo = sA_hi + TC_BM * 128;
         const uint32_t sW_hi = sA_lo + TC_BM * 128, sW_lo = sW_hi + BN * 128;
@@ -483,6 +505,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
       int stage = 0; uint32_t phase = 0;
       for (int it = it0; it < it1; ++it) {
         mbar_wait(&bar_full[stage], phase);
+        if (dbg && it == it0) s_stamp[3] = clock64();               // first operands landed
+        if (dbg && it == it1 - 1) s_stamp[4] = clock64();           // last operands landed
         tc_fence_after();
         const uint32_t sA_hi = smem0 + stage * STAGE, sA_lo = sA_hi + TC_BM * 128;
         const uint32_t sW_hi = sA_lo + TC_BM * 128, sW_lo = sW_hi + BN * 128;
@@ -507,6 +531,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
     const bool live = b < P.B;
     const size_t m = (size_t)b * g.L + tok;
     mbar_wait(&bar_acc, 0);
+    if (dbg && threadIdx.x == 64) s_stamp[5] = clock64();            // accumulator complete
     tc_fence_after();
     int p = 0, y = 0, x = 0;
     if ((P.resid && P.resid_mode != RS_NONE) || P.csum) tc_decode_tok(g, tok, p, y, x);
@@ -573,11 +598,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
       }
     }
   }
+  if (dbg && threadIdx.x == 64) s_stamp[6] = clock64();              // epilogue stores issued
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+  }
+  if (dbg && threadIdx.x == 0) {
+    const unsigned int slot = atomicAdd(&g_tc_dbg_count, 1u);
+    if (slot < g_tc_dbg_cap) {
+      long long* rec = g_tc_dbg + (size_t)slot * 16;
+      rec[0] = (long long)gridDim.x | ((long long)gridDim.y << 16) | ((long long)gridDim.z << 32);
+      rec[1] = (long long)(it1 - it0) | ((long long)P.taps << 16) | ((long long)P.Cin << 24) | ((long long)P.Cout << 40);
+      for (int i = 0; i < 7; ++i) rec[2 + i] = s_stamp[i];
+      rec[9] = clock64(); rec[10] = g_t0; rec[11] = gtime_ns();
+      unsigned int smid; asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+      rec[12] = smid; rec[13] = (long long)blockIdx.x | ((long long)blockIdx.y << 16) | ((long long)blockIdx.z << 32);
+    }
   }
 }
 

@@ -961,6 +961,15 @@ int mtv_debug_read(MtvHandle h, const char* tag, float* dst, int64_t dst_elems, 
   });
 }
 
+int mtv_debug_tc_timing(MtvHandle h, int64_t* records, int32_t cap, int32_t* count) {
+  return guarded([&] {
+    if (!h) throw MtvError("null handle");
+    CK(cudaSetDevice(h->cfg.device));
+    if (count) { unsigned int n = 0; CK(tc_debug_count(&n)); *count = (int32_t)n; }
+    CK(tc_debug_arm((long long*)records, records ? (unsigned int)cap : 0u));
+  });
+}
+
 int mtv_profile_forward(MtvHandle h, const float* x, const float* cond, const float* image_cond, int64_t image_cond_len,
                         const int64_t* t, int32_t B, float* out, MtvKernelTime* entries, int32_t cap, int32_t* n,
                         void* stream) {

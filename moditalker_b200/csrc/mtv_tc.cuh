@@ -59,5 +59,7 @@ cudaError_t launch_attn_tc(const AttnTcParams& P, cudaStream_t s);
 cudaError_t launch_apply_split(const ApplyParams& P, cudaStream_t s);
 cudaError_t launch_repack_split_w(const float* src, void* hi, void* lo, int Cout, int Cin, int taps, cudaStream_t s);
 cudaError_t launch_conv_tc(const TcConvParams& P, cudaStream_t s);
+cudaError_t tc_debug_arm(long long* buf, unsigned int cap);
+cudaError_t tc_debug_count(unsigned int* n);
 
 }  // namespace mtv
