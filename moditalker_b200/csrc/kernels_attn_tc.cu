@@ -105,6 +105,8 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 
 // ------------------------------------------------------------------ qkv -> split operands
 __global__ void __launch_bounds__(128) k_qkv_split(const __grid_constant__ QkvSplitParams P) {
+  MTV_PDL_TRIGGER();
+  MTV_PDL_WAIT();
   const int D = P.C / P.heads;
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;     // (b, head, token), token fastest
   const size_t total = (size_t)P.B * P.heads * P.L;
@@ -142,7 +144,7 @@ __global__ void __launch_bounds__(128) k_qkv_split(const __grid_constant__ QkvSp
 }
 cudaError_t launch_qkv_split(const QkvSplitParams& P, cudaStream_t s) {
   const size_t total = (size_t)P.B * P.heads * P.L;
-  k_qkv_split<<<(unsigned)((total + 127) / 128), 128, 0, s>>>(P);
+  { cudaError_t le_ = launch_k(k_qkv_split, dim3((unsigned)((total + 127) / 128)), dim3(128), (size_t)(0), s, P); if (le_ != cudaSuccess) return le_; }
   return cudaGetLastError();
 }
 
@@ -166,6 +168,7 @@ struct AttnSmem {
 template <int D>
 __global__ void __launch_bounds__(AT_THREADS, 1) k_attn_tc(const __grid_constant__ AttnTcParams P) {
   using SM = AttnSmem<D>;
+  MTV_PDL_TRIGGER();
   constexpr uint32_t IDESC_S = a_idesc(AT_BQ, AT_BKV);
   constexpr uint32_t IDESC_O = a_idesc(AT_BQ, D);
   constexpr int TMEM_COLS = 128;                           // S: cols [0,64), O block: cols [64, 64+D)
@@ -208,6 +211,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) k_attn_tc(const __grid_constant
   a_fence_after();
   const uint32_t tmem_base = tmem_base_s;
   const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 64;
+  MTV_PDL_WAIT();        // Q / K / V^T are written by the preceding k_qkv_split
 
   if (warp == 0) {
     // =============================== TMA producer ===============================
@@ -360,10 +364,27 @@ __global__ void __launch_bounds__(AT_THREADS, 1) k_attn_tc(const __grid_constant
     if (q < len) {
       const int b = bh / P.heads, h = bh - b * P.heads;
       const float inv = 1.0f / l_run;
-      float* dst = P.out + ((size_t)b * P.L + t_lo + q) * P.C + h * D;
+      const size_t oidx = ((size_t)b * P.L + t_lo + q) * P.C + h * D;
+      if (P.out_hi) {       // split-bf16 A operand of the proj_out GEMM, written in place of the fp32 tensor
+        __nv_bfloat16* oh = reinterpret_cast<__nv_bfloat16*>(P.out_hi) + oidx;
+        __nv_bfloat16* ol = reinterpret_cast<__nv_bfloat16*>(P.out_lo) + oidx;
 #pragma unroll
-      for (int d = 0; d < D; d += 4)
-        *reinterpret_cast<float4*>(dst + d) = make_float4(o[d] * inv, o[d + 1] * inv, o[d + 2] * inv, o[d + 3] * inv);
+        for (int d = 0; d < D; d += 8) {
+          __align__(16) __nv_bfloat16 hh[8], ll[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float val = o[d + i] * inv;
+            hh[i] = __float2bfloat16_rn(val); ll[i] = __float2bfloat16_rn(val - __bfloat162float(hh[i]));
+          }
+          *reinterpret_cast<uint4*>(oh + d) = *reinterpret_cast<const uint4*>(hh);
+          *reinterpret_cast<uint4*>(ol + d) = *reinterpret_cast<const uint4*>(ll);
+        }
+      } else {
+        float* dst = P.out + oidx;
+#pragma unroll
+        for (int d = 0; d < D; d += 4)
+          *reinterpret_cast<float4*>(dst + d) = make_float4(o[d] * inv, o[d + 1] * inv, o[d + 2] * inv, o[d + 3] * inv);
+      }
     }
   }
   a_fence_before();
@@ -382,7 +403,7 @@ static cudaError_t launch_attn_tc_d(const AttnTcParams& P, cudaStream_t s) {
   int nqb = 0;
   for (int i = 0; i < P.nseg; ++i) nqb += (P.seg_off[i + 1] - P.seg_off[i] + AT_BQ - 1) / AT_BQ;
   dim3 grid(nqb, P.B * P.heads);
-  k_attn_tc<D><<<grid, AT_THREADS, SM::TOTAL, s>>>(P);
+  { cudaError_t le_ = launch_k(k_attn_tc<D>, dim3(grid), dim3(AT_THREADS), (size_t)(SM::TOTAL), s, P); if (le_ != cudaSuccess) return le_; }
   return cudaGetLastError();
 }
 

@@ -9,8 +9,11 @@
 // kernels_tc.cu and are cross-checked against these in tests/test_kernels_gpu.py.
 #include "mtv_kernels.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 namespace mtv {
+
+int g_mtv_use_pdl = [] { const char* e = getenv("MTV_NO_PDL"); return (e && e[0] == '1') ? 0 : 1; }();
 
 // ------------------------------------------------------------------ token geometry
 __device__ __forceinline__ void decode_tok(const Geo& g, int tok, int& p, int& y, int& x) {
@@ -64,6 +67,8 @@ __device__ __forceinline__ void store_out(const ConvParams& P, int b, int tok, i
 template <int BM, int BN, int TM, int TN>
 __global__ void __launch_bounds__((BM / TM) * (BN / TN))
 k_conv_simt(const __grid_constant__ ConvParams P) {
+  MTV_PDL_TRIGGER();
+  MTV_PDL_WAIT();
   constexpr int NT = (BM / TM) * (BN / TN);
   constexpr int BK = 16;
   constexpr int LDA = BM + 4;
@@ -233,6 +238,8 @@ k_conv_simt(const __grid_constant__ ConvParams P) {
 
 // Deterministic split-K reduction + epilogue (fixed summation order over splits).
 __global__ void k_splitk_epilogue(const __grid_constant__ ConvParams P) {
+  MTV_PDL_TRIGGER();
+  MTV_PDL_WAIT();
   const Geo g = P.geo;
   const size_t M = (size_t)P.B * g.L;
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -284,19 +291,19 @@ cudaError_t launch_conv_simt(const ConvParams& P, cudaStream_t s) {
   const int ks = P.ksplit > 1 ? P.ksplit : 1;
   if (P.Cout <= 16) {
     dim3 grid((M + 63) / 64, (P.Cout + 15) / 16, ks);
-    k_conv_simt<64, 16, 4, 1><<<grid, 256, 0, s>>>(P);
+    { cudaError_t le_ = launch_k(k_conv_simt<64, 16, 4, 1>, dim3(grid), dim3(256), (size_t)(0), s, P); if (le_ != cudaSuccess) return le_; }
   } else if (conv_bm(P, sms) == 64) {
     dim3 grid((M + 63) / 64, (P.Cout + 63) / 64, ks);
-    k_conv_simt<64, 64, 4, 4><<<grid, 256, 0, s>>>(P);
+    { cudaError_t le_ = launch_k(k_conv_simt<64, 64, 4, 4>, dim3(grid), dim3(256), (size_t)(0), s, P); if (le_ != cudaSuccess) return le_; }
   } else {
     dim3 grid((M + 31) / 32, (P.Cout + 63) / 64, ks);
-    k_conv_simt<32, 64, 2, 4><<<grid, 256, 0, s>>>(P);
+    { cudaError_t le_ = launch_k(k_conv_simt<32, 64, 2, 4>, dim3(grid), dim3(256), (size_t)(0), s, P); if (le_ != cudaSuccess) return le_; }
   }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   if (ks > 1) {
     const size_t tot = (size_t)M * P.Cout;
-    k_splitk_epilogue<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(P);
+    { cudaError_t le_ = launch_k(k_splitk_epilogue, dim3((unsigned)((tot + 255) / 256)), dim3(256), (size_t)(0), s, P); if (le_ != cudaSuccess) return le_; }
     e = cudaGetLastError();
   }
   return e;
@@ -309,6 +316,8 @@ cudaError_t launch_conv_simt(const ConvParams& P, cudaStream_t s) {
 // h*(1+scale)+shift (unet.py:201-202) folded in.  Sums are fp32 per thread over <= chunk
 // tokens, fp64 across threads / CTAs (atomics), finalised by the last CTA of a segment.
 __global__ void __launch_bounds__(256) k_gn_stats(const __grid_constant__ GnParams P) {
+  MTV_PDL_TRIGGER();
+  MTV_PDL_WAIT();
   __shared__ double s_sum[32][2];
   __shared__ bool s_last;
   const int tid = threadIdx.x;
@@ -372,7 +381,7 @@ cudaError_t launch_gn_stats(const GnParams& P, cudaStream_t s) {
   int maxlen = 0;
   for (int i = 0; i < P.nseg; ++i) maxlen = max(maxlen, P.seg_off[i + 1] - P.seg_off[i]);
   dim3 grid((maxlen + P.chunk_tokens - 1) / P.chunk_tokens, P.B * P.nseg);
-  k_gn_stats<<<grid, 256, 0, s>>>(P);
+  { cudaError_t le_ = launch_k(k_gn_stats, dim3(grid), dim3(256), (size_t)(0), s, P); if (le_ != cudaSuccess) return le_; }
   return cudaGetLastError();
 }
 
@@ -384,6 +393,8 @@ cudaError_t launch_gn_stats(const GnParams& P, cudaStream_t s) {
 // materialised: 64-query x 64-key tiles with an online softmax.
 template <int D>
 __global__ void __launch_bounds__(256) k_attn_simt(const __grid_constant__ AttnParams P) {
+  MTV_PDL_TRIGGER();
+  MTV_PDL_WAIT();
   constexpr int BQ = 64, BKV = 64, LD = 68;
   constexpr int CD = D / 16;                      // output columns per thread
   extern __shared__ __align__(16) float smem[];
@@ -516,7 +527,7 @@ static cudaError_t launch_attn_d(const AttnParams& P, cudaStream_t s) {
   int nqb = 0;
   for (int i = 0; i < P.nseg; ++i) nqb += (P.seg_off[i + 1] - P.seg_off[i] + 63) / 64;
   dim3 grid(nqb, P.B * P.heads);
-  k_attn_simt<D><<<grid, 256, smem, s>>>(P);
+  { cudaError_t le_ = launch_k(k_attn_simt<D>, dim3(grid), dim3(256), (size_t)(smem), s, P); if (le_ != cudaSuccess) return le_; }
   return cudaGetLastError();
 }
 
@@ -536,6 +547,8 @@ cudaError_t launch_attn_simt(const AttnParams& P, cudaStream_t s) {
 // (unet.py:701-705, 1011-1012) -> every ResBlock's emb_layers = Linear(SiLU(emb))
 // (unet.py:148-154, 193) in one batched GEMV.  One warp per output feature.
 __global__ void k_temb(const __grid_constant__ EmbParams P) {
+  MTV_PDL_TRIGGER();
+  MTV_PDL_WAIT();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int half = P.mc / 2;
   if (i >= P.B * half) return;
@@ -549,6 +562,8 @@ __global__ void k_temb(const __grid_constant__ EmbParams P) {
 __global__ void __launch_bounds__(256) k_linear_warp(const float* __restrict__ W, const float* __restrict__ bias,
                                                      const float* __restrict__ in, float* __restrict__ out,
                                                      int J, int K, int B, int silu_out) {
+  MTV_PDL_TRIGGER();
+  MTV_PDL_WAIT();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= J) return;
   const float* w = W + (size_t)warp * K;
@@ -570,11 +585,11 @@ __global__ void __launch_bounds__(256) k_linear_warp(const float* __restrict__ W
 
 cudaError_t launch_emb(const EmbParams& P, cudaStream_t s) {
   const int n = P.B * (P.mc / 2);
-  k_temb<<<(n + 127) / 128, 128, 0, s>>>(P);
-  k_linear_warp<<<(P.ted * 32 + 255) / 256, 256, 0, s>>>(P.w1, P.b1, P.temb, P.h1, P.ted, P.mc, P.B, 1);
+  { cudaError_t le_ = launch_k(k_temb, dim3((n + 127) / 128), dim3(128), (size_t)(0), s, P); if (le_ != cudaSuccess) return le_; }
+  { cudaError_t le_ = launch_k(k_linear_warp, dim3((P.ted * 32 + 255) / 256), dim3(256), (size_t)(0), s, P.w1, P.b1, P.temb, P.h1, P.ted, P.mc, P.B, 1); if (le_ != cudaSuccess) return le_; }
   // emb is only ever consumed through SiLU (every emb_layers starts with nn.SiLU) -> store silu(emb)
-  k_linear_warp<<<(P.ted * 32 + 255) / 256, 256, 0, s>>>(P.w2, P.b2, P.h1, P.semb, P.ted, P.ted, P.B, 1);
-  k_linear_warp<<<(unsigned)(((size_t)P.J * 32 + 255) / 256), 256, 0, s>>>(P.wall, P.ball, P.semb, P.film, P.J, P.ted, P.B, 0);
+  { cudaError_t le_ = launch_k(k_linear_warp, dim3((P.ted * 32 + 255) / 256), dim3(256), (size_t)(0), s, P.w2, P.b2, P.h1, P.semb, P.ted, P.ted, P.B, 1); if (le_ != cudaSuccess) return le_; }
+  { cudaError_t le_ = launch_k(k_linear_warp, dim3((unsigned)(((size_t)P.J * 32 + 255) / 256)), dim3(256), (size_t)(0), s, P.wall, P.ball, P.semb, P.film, P.J, P.ted, P.B, 0); if (le_ != cudaSuccess) return le_; }
   return cudaGetLastError();
 }
 

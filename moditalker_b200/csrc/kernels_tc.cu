@@ -35,7 +35,21 @@ __device__ __forceinline__ void tc_decode_tok(const Geo& g, int tok, int& p, int
 }
 __device__ __forceinline__ int tc_plane_off(const Geo& g, int p) { return p == 0 ? 0 : g.res * g.res + (p - 1) * g.t * g.res; }
 
+__device__ __forceinline__ void tc_store_split(const float4& v, void* hi_base, void* lo_base, size_t o) {
+  const float f[4] = {v.x, v.y, v.z, v.w};
+  __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    hi[i] = __float2bfloat16_rn(f[i]);
+    lo[i] = __float2bfloat16_rn(f[i] - __bfloat162float(hi[i]));
+  }
+  *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(hi_base) + o) = *reinterpret_cast<const uint2*>(hi);
+  *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(lo_base) + o) = *reinterpret_cast<const uint2*>(lo);
+}
+
 __global__ void __launch_bounds__(256) k_apply_split(const __grid_constant__ ApplyParams P) {
+  MTV_PDL_TRIGGER();
+  MTV_PDL_WAIT();
   const int C = P.C0 + P.C1;
   const int cq = C >> 2;
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -58,34 +72,31 @@ __global__ void __launch_bounds__(256) k_apply_split(const __grid_constant__ App
     if (P.silu) { v.x = silu_tc(v.x); v.y = silu_tc(v.y); v.z = silu_tc(v.z); v.w = silu_tc(v.w); }
     return v;
   };
-  float4 v;
+  float4 v, rw;
   if (P.resample == RS_NONE) {
-    v = xf(__ldg(reinterpret_cast<const float4*>(src + ((size_t)b * P.geo.L + tok) * Cs + cc)));
+    rw = __ldg(reinterpret_cast<const float4*>(src + ((size_t)b * P.geo.L + tok) * Cs + cc));
+    v = xf(rw);
   } else if (P.resample == RS_UP2) {
     const Geo gs = geo_down(P.geo);
     const int ts = tc_plane_off(gs, p) + (y >> 1) * gs.res + (x >> 1);
-    v = xf(__ldg(reinterpret_cast<const float4*>(src + ((size_t)b * gs.L + ts) * Cs + cc)));
+    rw = __ldg(reinterpret_cast<const float4*>(src + ((size_t)b * gs.L + ts) * Cs + cc));
+    v = xf(rw);
   } else {
     const Geo gs = geo_up(P.geo);
     const int ts = tc_plane_off(gs, p) + (2 * y) * gs.res + 2 * x;
     const float* q = src + ((size_t)b * gs.L + ts) * Cs + cc;
-    const float4 v0 = xf(__ldg(reinterpret_cast<const float4*>(q)));
-    const float4 v1 = xf(__ldg(reinterpret_cast<const float4*>(q + Cs)));
-    const float4 v2 = xf(__ldg(reinterpret_cast<const float4*>(q + (size_t)gs.res * Cs)));
-    const float4 v3 = xf(__ldg(reinterpret_cast<const float4*>(q + (size_t)(gs.res + 1) * Cs)));
+    const float4 w0 = __ldg(reinterpret_cast<const float4*>(q)), w1 = __ldg(reinterpret_cast<const float4*>(q + Cs));
+    const float4 w2 = __ldg(reinterpret_cast<const float4*>(q + (size_t)gs.res * Cs));
+    const float4 w3 = __ldg(reinterpret_cast<const float4*>(q + (size_t)(gs.res + 1) * Cs));
+    const float4 v0 = xf(w0), v1 = xf(w1), v2 = xf(w2), v3 = xf(w3);
     v.x = 0.25f * ((v0.x + v1.x) + (v2.x + v3.x)); v.y = 0.25f * ((v0.y + v1.y) + (v2.y + v3.y));
     v.z = 0.25f * ((v0.z + v1.z) + (v2.z + v3.z)); v.w = 0.25f * ((v0.w + v1.w) + (v2.w + v3.w));
-  }
-  const float f[4] = {v.x, v.y, v.z, v.w};
-  __nv_bfloat16 hi[4], lo[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    hi[i] = __float2bfloat16_rn(f[i]);
-    lo[i] = __float2bfloat16_rn(f[i] - __bfloat162float(hi[i]));
+    rw.x = 0.25f * ((w0.x + w1.x) + (w2.x + w3.x)); rw.y = 0.25f * ((w0.y + w1.y) + (w2.y + w3.y));
+    rw.z = 0.25f * ((w0.z + w1.z) + (w2.z + w3.z)); rw.w = 0.25f * ((w0.w + w1.w) + (w2.w + w3.w));
   }
   const size_t o = m * C + c;
-  *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(P.hi) + o) = *reinterpret_cast<const uint2*>(hi);
-  *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(P.lo) + o) = *reinterpret_cast<const uint2*>(lo);
+  tc_store_split(v, P.hi, P.lo, o);
+  if (P.raw_hi) tc_store_split(rw, P.raw_hi, P.raw_lo, o);
 }
 
 // GroupNorm32 finalise + apply in ONE kernel: group statistics come from the per-channel sums the
@@ -94,6 +105,8 @@ __global__ void __launch_bounds__(256) k_apply_split(const __grid_constant__ App
 // the sums of that (sample, plane | all planes) into the per-channel affine in shared memory
 // (FiLM folded in), then the body is k_apply_split's.
 __global__ void __launch_bounds__(256) k_apply_norm_split(const __grid_constant__ ApplyParams P) {
+  MTV_PDL_TRIGGER();
+  MTV_PDL_WAIT();
   extern __shared__ float s_aff[];                 // a[C] | d[C]
   __shared__ double s_mean[32], s_rstd[32];
   const int C = P.C0 + P.C1, cpg = C / 32;
@@ -156,32 +169,29 @@ __global__ void __launch_bounds__(256) k_apply_norm_split(const __grid_constant_
       if (P.silu) { v.x = silu_tc(v.x); v.y = silu_tc(v.y); v.z = silu_tc(v.z); v.w = silu_tc(v.w); }
       return v;
     };
-    float4 v;
+    float4 v, rw;
     if (P.resample == RS_NONE) {
-      v = xf(__ldg(reinterpret_cast<const float4*>(src + ((size_t)b * g.L + tok) * Cs + cc)));
+      rw = __ldg(reinterpret_cast<const float4*>(src + ((size_t)b * g.L + tok) * Cs + cc));
+      v = xf(rw);
     } else if (P.resample == RS_UP2) {
       const int ts = tc_plane_off(gs, p) + (y >> 1) * gs.res + (x >> 1);
-      v = xf(__ldg(reinterpret_cast<const float4*>(src + ((size_t)b * gs.L + ts) * Cs + cc)));
+      rw = __ldg(reinterpret_cast<const float4*>(src + ((size_t)b * gs.L + ts) * Cs + cc));
+      v = xf(rw);
     } else {
       const int ts = tc_plane_off(gs, p) + (2 * y) * gs.res + 2 * x;
       const float* q = src + ((size_t)b * gs.L + ts) * Cs + cc;
-      const float4 v0 = xf(__ldg(reinterpret_cast<const float4*>(q)));
-      const float4 v1 = xf(__ldg(reinterpret_cast<const float4*>(q + Cs)));
-      const float4 v2 = xf(__ldg(reinterpret_cast<const float4*>(q + (size_t)gs.res * Cs)));
-      const float4 v3 = xf(__ldg(reinterpret_cast<const float4*>(q + (size_t)(gs.res + 1) * Cs)));
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(q)), w1 = __ldg(reinterpret_cast<const float4*>(q + Cs));
+      const float4 w2 = __ldg(reinterpret_cast<const float4*>(q + (size_t)gs.res * Cs));
+      const float4 w3 = __ldg(reinterpret_cast<const float4*>(q + (size_t)(gs.res + 1) * Cs));
+      const float4 v0 = xf(w0), v1 = xf(w1), v2 = xf(w2), v3 = xf(w3);
       v.x = 0.25f * ((v0.x + v1.x) + (v2.x + v3.x)); v.y = 0.25f * ((v0.y + v1.y) + (v2.y + v3.y));
       v.z = 0.25f * ((v0.z + v1.z) + (v2.z + v3.z)); v.w = 0.25f * ((v0.w + v1.w) + (v2.w + v3.w));
-    }
-    const float f[4] = {v.x, v.y, v.z, v.w};
-    __nv_bfloat16 hi[4], lo[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      hi[i] = __float2bfloat16_rn(f[i]);
-      lo[i] = __float2bfloat16_rn(f[i] - __bfloat162float(hi[i]));
+      rw.x = 0.25f * ((w0.x + w1.x) + (w2.x + w3.x)); rw.y = 0.25f * ((w0.y + w1.y) + (w2.y + w3.y));
+      rw.z = 0.25f * ((w0.z + w1.z) + (w2.z + w3.z)); rw.w = 0.25f * ((w0.w + w1.w) + (w2.w + w3.w));
     }
     const size_t o = ((size_t)b * g.L + tok) * C + c;
-    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(P.hi) + o) = *reinterpret_cast<const uint2*>(hi);
-    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(P.lo) + o) = *reinterpret_cast<const uint2*>(lo);
+    tc_store_split(v, P.hi, P.lo, o);
+    if (P.raw_hi) tc_store_split(rw, P.raw_hi, P.raw_lo, o);
   }
 }
 
@@ -191,11 +201,11 @@ cudaError_t launch_apply_split(const ApplyParams& P, cudaStream_t s) {
     const int maxp = P.geo.res * P.geo.res;
     dim3 grid((maxp + P.chunk_tokens - 1) / P.chunk_tokens, 3, P.B);
     const size_t smem = (size_t)C * 2 * sizeof(float);
-    k_apply_norm_split<<<grid, 256, smem, s>>>(P);
+    { cudaError_t le_ = launch_k(k_apply_norm_split, dim3(grid), dim3(256), (size_t)(smem), s, P); if (le_ != cudaSuccess) return le_; }
     return cudaGetLastError();
   }
   const size_t total = (size_t)P.B * P.geo.L * ((P.C0 + P.C1) / 4);
-  k_apply_split<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(P);
+  { cudaError_t le_ = launch_k(k_apply_split, dim3((unsigned)((total + 255) / 256)), dim3(256), (size_t)(0), s, P); if (le_ != cudaSuccess) return le_; }
   return cudaGetLastError();
 }
 
@@ -435,6 +445,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
   __shared__ __align__(8) uint64_t bar_full[NS], bar_empty[NS], bar_acc;
   __shared__ uint32_t tmem_base_s;
   __shared__ long long s_stamp[8];
+  MTV_PDL_TRIGGER();
   const bool dbg = g_tc_dbg != nullptr;
   long long g_t0 = 0;
   if (dbg && threadIdx.x == 0) { s_stamp[0] = clock64(); g_t0 = gtime_ns(); }
@@ -476,26 +487,46 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
   if (warp == 0) {
     // =============================== TMA producer ===============================
     if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      for (int it = it0; it < it1; ++it) {
-        mbar_wait(&bar_empty[stage], phase ^ 1u);
-        if (dbg && it == it1 - 1) s_stamp[2] = clock64();          // last stage request issued
-        mbar_expect_tx(&bar_full[stage], (uint32_t)STAGE);
-        const uint32_t sA_hi = smem0 + stage * STAGE, sA_lo = sA_hi + TC_BM * 128;
-        const uint32_t sW_hi = sA_lo + TC_BM * 128, sW_lo = sW_hi + BN * 128;
+      auto load_W = [&](int it, int stage) {
+        const uint32_t sW_hi = smem0 + stage * STAGE + 2 * TC_BM * 128, sW_lo = sW_hi + BN * 128;
         const uint32_t fb = smem_u32(&bar_full[stage]);
-        if (it >= it_main) {           // second K-segment: 1x1 conv of the skip operand
+        if (it >= it_main) {
           const int c2 = (it - it_main) * TC_BK;
-          tc_load_A(g, T, P.tmA2_hi, P.tmA2_lo, 1, 0, c2, sA_hi, sA_lo, fb);
           tma_load_2d(sW_hi, &P.tmW2_hi, fb, c2, n0);
           tma_load_2d(sW_lo, &P.tmW2_lo, fb, c2, n0);
         } else {
-          const int tap = it / kch, kc = it - tap * kch;
-          const int c0 = kc * TC_BK;
-          tc_load_A(g, T, P.tmA_hi, P.tmA_lo, P.taps, tap, c0, sA_hi, sA_lo, fb);
+          const int tap = it / kch, c0 = (it - tap * kch) * TC_BK;
           tma_load_2d(sW_hi, &P.tmW_hi, fb, c0, tap * P.Cout + n0);
           tma_load_2d(sW_lo, &P.tmW_lo, fb, c0, tap * P.Cout + n0);
         }
+      };
+      auto load_A = [&](int it, int stage) {
+        const uint32_t sA_hi = smem0 + stage * STAGE, sA_lo = sA_hi + TC_BM * 128;
+        const uint32_t fb = smem_u32(&bar_full[stage]);
+        if (it >= it_main) {           // second K-segment: 1x1 conv of the skip operand
+          tc_load_A(g, T, P.tmA2_hi, P.tmA2_lo, 1, 0, (it - it_main) * TC_BK, sA_hi, sA_lo, fb);
+        } else {
+          const int tap = it / kch, c0 = (it - tap * kch) * TC_BK;
+          tc_load_A(g, T, P.tmA_hi, P.tmA_lo, P.taps, tap, c0, sA_hi, sA_lo, fb);
+        }
+      };
+      // Weights do not depend on the previous kernel: fill the ring's W halves BEFORE the grid
+      // dependency resolves (overlaps their HBM latency with the predecessor's tail) ...
+      const int npre = min(NS, it1 - it0);
+      for (int i = 0; i < npre; ++i) {
+        mbar_expect_tx(&bar_full[i], (uint32_t)STAGE);
+        load_W(it0 + i, i);
+      }
+      MTV_PDL_WAIT();                  // ... the activation operand does
+      int stage = 0; uint32_t phase = 0;
+      for (int it = it0; it < it1; ++it) {
+        if (it - it0 >= npre) {
+          mbar_wait(&bar_empty[stage], phase ^ 1u);
+          mbar_expect_tx(&bar_full[stage], (uint32_t)STAGE);
+          load_W(it, stage);
+        }
+        if (dbg && it == it1 - 1) s_stamp[2] = clock64();          // last stage request issued
+        load_A(it, stage);
         if (++stage == NS) { stage = 0; phase ^= 1u; }
       }
     }
@@ -530,6 +561,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
     int b, tok; tc_row_map(T, row, b, tok);
     const bool live = b < P.B;
     const size_t m = (size_t)b * g.L + tok;
+    MTV_PDL_WAIT();                                 // residual / statistics buffers belong to earlier kernels
+    // the residual and bias of the first 32-column chunk are fetched while the MMAs still run
+    const bool pre_res = live && P.resid && P.resid_mode == RS_NONE && P.ksplit <= 1;
+    float4 rpre[8];
+    if (pre_res) {
+      const float4* rp4 = reinterpret_cast<const float4*>(P.resid + m * P.Cout + n0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) rpre[j] = __ldg(rp4 + j);
+    }
     mbar_wait(&bar_acc, 0);
     if (dbg && threadIdx.x == 64) s_stamp[5] = clock64();            // accumulator complete
     tc_fence_after();
@@ -542,6 +582,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
       __syncwarp();
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
       const int n = n0 + c0;
+      float4 rnext[8];
+      const bool have_next = pre_res && (c0 + 32 < BN);
+      if (have_next) {
+        const float4* rp4 = reinterpret_cast<const float4*>(P.resid + m * P.Cout + n + 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) rnext[j] = __ldg(rp4 + j);
+      }
       if (!live) {
         // rows of samples beyond the batch (partial last tile of a small level): nothing to store
       } else if (P.ksplit > 1) {
@@ -562,7 +609,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
           }
           if (P.resid) {
             if (P.resid_mode == RS_NONE) {
-              const float4 rv = __ldg(reinterpret_cast<const float4*>(P.resid + m * P.Cout + n + j));
+              const float4 rv = rpre[j >> 2];
               v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
             } else if (P.resid_mode == RS_UP2) {
               const Geo gs = geo_down(g);
@@ -581,8 +628,41 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
               v.z += 0.25f * (r0.z + r1.z + r2.z + r3.z); v.w += 0.25f * (r0.w + r1.w + r2.w + r3.w);
             }
           }
-          *reinterpret_cast<float4*>(dst + j) = v;
+          if (!P.qkv_heads) *reinterpret_cast<float4*>(dst + j) = v;
           fv[j] = v.x; fv[j + 1] = v.y; fv[j + 2] = v.z; fv[j + 3] = v.w;
+        }
+        if (P.qkv_heads) {
+          // channels are head-major [h: q(D) k(D) v(D)] (unet.py:321); D >= 16, so every aligned run of 16
+          // channels is one of q / k / v of one head
+          const int Dh = P.Cout / (3 * P.qkv_heads);
+          const float qs = 1.4426950408889634f * rsqrtf((float)Dh);
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            const int nn = n + hf * 16;
+            const int hd = nn / (3 * Dh), rr = nn - hd * 3 * Dh;
+            const int kind = rr / Dh, d0 = rr - kind * Dh;
+            const size_t bh = (size_t)b * P.qkv_heads + hd;
+            __align__(16) __nv_bfloat16 hh[16], ll[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float val = kind == 0 ? fv[hf * 16 + i] * qs : fv[hf * 16 + i];
+              hh[i] = __float2bfloat16_rn(val);
+              ll[i] = __float2bfloat16_rn(val - __bfloat162float(hh[i]));
+            }
+            if (kind < 2) {
+              __nv_bfloat16* ph = reinterpret_cast<__nv_bfloat16*>(kind == 0 ? P.q_hi : P.k_hi) + (bh * g.L + tok) * Dh + d0;
+              __nv_bfloat16* pw = reinterpret_cast<__nv_bfloat16*>(kind == 0 ? P.q_lo : P.k_lo) + (bh * g.L + tok) * Dh + d0;
+              reinterpret_cast<uint4*>(ph)[0] = reinterpret_cast<const uint4*>(hh)[0];
+              reinterpret_cast<uint4*>(ph)[1] = reinterpret_cast<const uint4*>(hh)[1];
+              reinterpret_cast<uint4*>(pw)[0] = reinterpret_cast<const uint4*>(ll)[0];
+              reinterpret_cast<uint4*>(pw)[1] = reinterpret_cast<const uint4*>(ll)[1];
+            } else {
+              __nv_bfloat16* ph = reinterpret_cast<__nv_bfloat16*>(P.vt_hi) + (bh * Dh + d0) * g.L + tok;
+              __nv_bfloat16* pw = reinterpret_cast<__nv_bfloat16*>(P.vt_lo) + (bh * Dh + d0) * g.L + tok;
+#pragma unroll
+              for (int i = 0; i < 16; ++i) { ph[(size_t)i * g.L] = hh[i]; pw[(size_t)i * g.L] = ll[i]; }
+            }
+          }
         }
         if (P.csum) {   // uniform branch: statistics of the tensor just written, for the next GroupNorm
 #pragma unroll
@@ -595,6 +675,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
         for (int j = 0; j < 32; ++j) fv[j] = __uint_as_float(r[j]);
         __syncwarp();
         tc_csum_chunk(fv, live, lane, P.csum + (((size_t)(live ? b : 0) * 3 + pl_stat) * P.Cout + n) * 2);
+      }
+      if (have_next) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) rpre[j] = rnext[j];
       }
     }
   }
@@ -623,6 +707,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
 // channels: warp w = channel quad, lane = row, so the per-channel statistics reduce with three
 // shuffles over aligned 8-row groups (never straddling a (sample, plane) boundary).
 __global__ void __launch_bounds__(256) k_tc_splitk_epilogue(const __grid_constant__ TcConvParams P) {
+  MTV_PDL_TRIGGER();
+  MTV_PDL_WAIT();
   const Geo g = P.geo;
   const size_t M = (size_t)P.B * g.L;
   const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
@@ -684,17 +770,17 @@ cudaError_t launch_conv_tc(const TcConvParams& P, cudaStream_t s) {
   if (BN == 64) {
     e = cudaFuncSetAttribute(k_conv_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(64));
     if (e != cudaSuccess) return e;
-    k_conv_tc<64><<<grid, TC_THREADS, tc_smem_bytes(64), s>>>(P);
+    { cudaError_t le_ = launch_k(k_conv_tc<64>, dim3(grid), dim3(TC_THREADS), (size_t)(tc_smem_bytes(64)), s, P); if (le_ != cudaSuccess) return le_; }
   } else {
     e = cudaFuncSetAttribute(k_conv_tc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(128));
     if (e != cudaSuccess) return e;
-    k_conv_tc<128><<<grid, TC_THREADS, tc_smem_bytes(128), s>>>(P);
+    { cudaError_t le_ = launch_k(k_conv_tc<128>, dim3(grid), dim3(TC_THREADS), (size_t)(tc_smem_bytes(128)), s, P); if (le_ != cudaSuccess) return le_; }
   }
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   if (P.ksplit > 1) {
     dim3 rgrid(M / 32, P.Cout / 32);
-    k_tc_splitk_epilogue<<<rgrid, 256, 0, s>>>(P);
+    { cudaError_t le_ = launch_k(k_tc_splitk_epilogue, dim3(rgrid), dim3(256), (size_t)(0), s, P); if (le_ != cudaSuccess) return le_; }
     e = cudaGetLastError();
   }
   return e;

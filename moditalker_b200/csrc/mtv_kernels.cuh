@@ -12,8 +12,30 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <utility>
+
+// Programmatic dependent launch: every kernel of the forward is launched with the
+// programmatic-stream-serialization attribute, triggers its dependents at entry and executes
+// griddepcontrol.wait before it first touches memory written by its predecessor, so launch latency
+// and kernel prologues (barrier init, TMEM allocation, weight TMA requests) overlap the tail of the
+// previous kernel.  Both instructions are no-ops when the attribute is absent.
+#define MTV_PDL_TRIGGER() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
+#define MTV_PDL_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
 
 namespace mtv {
+
+extern int g_mtv_use_pdl;   // 1 unless MTV_NO_PDL=1 (kernels_simt.cu)
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = g_mtv_use_pdl ? 1 : 0;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
 
 struct Geo {   // tri-plane token geometry of one pyramid level
   int res;     // xy plane: res x res

@@ -160,7 +160,7 @@ struct MtvHandle_t {
   std::map<int, std::unique_ptr<Plan>> plans;
   Plan* last_plan = nullptr;
   int64_t weight_bytes = 0;
-  int tc_mask = 0x1ff;
+  int tc_mask = 0x3ff;
   cudaStream_t cap_stream = nullptr;
   cudaStream_t capture_stream() {
     if (!cap_stream) CK(cudaStreamCreateWithFlags(&cap_stream, cudaStreamNonBlocking));
@@ -297,6 +297,13 @@ CUtensorMap make_tmap_bf16(void* base, int rank, const uint64_t* dims, const uin
 
 // ------------------------------------------------------------------ plan builder
 struct NormRef { float* a = nullptr; float* d = nullptr; int nseg = 0; };
+struct SplitBuf { void* hi = nullptr; void* lo = nullptr; };
+struct TcOpts {
+  const SplitBuf* pre0 = nullptr;     // seg0 operand already exists (e.g. written by the attention kernel)
+  const SplitBuf* pre1 = nullptr;     // seg1 (skip) operand already exists
+  SplitBuf* raw_out = nullptr;        // ask seg0's apply kernel to also emit the raw split of its source
+  const QkvSplitParams* qkv = nullptr;  // qkv GEMM: epilogue writes the attention operands instead of fp32
+};
 
 struct Builder {
   MtvHandle_t* h; Plan* pl; int B;
@@ -370,6 +377,7 @@ struct Builder {
   bool fuse_gn() const { return h->cfg.kernel_path != 1 && ((h->tc_mask >> 8) & 1); }
 
   // ---- tensor-core lowering -------------------------------------------------------------
+  bool tc_ok_pb(ConvParams P) const { P.B = B; return tc_ok(P); }
   bool tc_ok(const ConvParams& P) const {
     if (h->cfg.kernel_path == 1 || P.out_chmajor) return false;
     if (P.Cout % 64) return false;
@@ -389,14 +397,15 @@ struct Builder {
     }
     return true;
   }
-  // split-bf16 operand of one K-segment + its TMA maps
-  void tc_operand(const std::string& name, const KSeg& S, const Geo& g, CUtensorMap* a_hi, CUtensorMap* a_lo, int norm_id) {
+  // split-bf16 operand of one K-segment (+ optionally the un-normalised split of the same source)
+  SplitBuf emit_apply(const std::string& name, const KSeg& S, const Geo& g, int norm_id, SplitBuf* raw_out) {
     const int C = S.C0 + S.C1;
     const size_t bytes = (size_t)B * g.L * C * 2;
-    void* hi = dalloc(bytes); void* lo = dalloc(bytes);
+    SplitBuf out; out.hi = dalloc(bytes); out.lo = dalloc(bytes);
     ApplyParams A{};
     A.src0 = S.src0; A.src1 = S.src1; A.C0 = S.C0; A.C1 = S.C1;
-    A.silu = S.silu; A.resample = S.resample; A.B = B; A.geo = g; A.hi = hi; A.lo = lo;
+    A.silu = S.silu; A.resample = S.resample; A.B = B; A.geo = g; A.hi = out.hi; A.lo = out.lo;
+    if (raw_out) { raw_out->hi = dalloc(bytes); raw_out->lo = dalloc(bytes); A.raw_hi = raw_out->hi; A.raw_lo = raw_out->lo; }
     if (norm_id >= 0) {
       const NormSpec& n = norms[norm_id];
       if (fuse_gn() && n.x0.csum && (!n.has_x1 || n.x1.csum)) {
@@ -409,20 +418,23 @@ struct Builder {
         A.nrm_a = r.a; A.nrm_d = r.d; A.nrm_nseg = r.nseg;
       }
     }
-    Op op; op.name = "apply:" + name; op.bytes = (double)B * g.L * C * 8;
+    Op op; op.name = "apply:" + name; op.bytes = (double)B * g.L * C * (raw_out ? 12 : 8);
     op.fn = [A](cudaStream_t s) { return launch_apply_split(A, s); };
     pl->ops.push_back(op);
-    void* ptr[2] = {hi, lo}; CUtensorMap* dst[2] = {a_hi, a_lo};
+    return out;
+  }
+  void make_A_maps(const SplitBuf& buf, int C, int taps, const Geo& g, CUtensorMap* a_hi, CUtensorMap* a_lo) {
+    void* ptr[2] = {buf.hi, buf.lo}; CUtensorMap* dst[2] = {a_hi, a_lo};
     const bool small = g.L <= 128;
     const uint32_t spt = small ? (uint32_t)(128 / g.L) : 1u;          // samples per tile (kernels_tc.cu: tc_tile)
     const uint64_t rowb = (uint64_t)C * 2;
     for (int k = 0; k < 2; ++k) {
       char* base = (char*)ptr[k];
-      if (S.taps == 1 && !small) {
+      if (taps == 1 && !small) {
         const uint64_t dims[2] = {(uint64_t)C, (uint64_t)B * g.L}; const uint64_t str[1] = {rowb};
         const uint32_t box[2] = {64, 128};
         dst[k][0] = make_tmap_bf16(base, 2, dims, str, box);
-      } else if (S.taps == 1) {
+      } else if (taps == 1) {
         const uint64_t dims[3] = {(uint64_t)C, (uint64_t)g.L, (uint64_t)B}; const uint64_t str[2] = {rowb, rowb * g.L};
         const uint32_t box0[3] = {64, (uint32_t)(g.res * g.res), spt}, box1[3] = {64, (uint32_t)(g.t * g.res), spt};
         dst[k][0] = make_tmap_bf16(base, 3, dims, str, box0);
@@ -445,18 +457,26 @@ struct Builder {
       }
     }
   }
-  void conv_tc(const std::string& name, const ConvParams& P, int norm0, int norm1, Tensor* out_t) {
+  void conv_tc(const std::string& name, const ConvParams& P, int norm0, int norm1, Tensor* out_t, const TcOpts& o) {
     TcConvParams T{};
     if (out_t && fuse_gn()) { out_t->csum = alloc_csum(P.Cout); T.csum = out_t->csum; }
+    if (o.qkv) {
+      T.qkv_heads = o.qkv->heads;
+      T.q_hi = o.qkv->q_hi; T.q_lo = o.qkv->q_lo; T.k_hi = o.qkv->k_hi; T.k_lo = o.qkv->k_lo;
+      T.vt_hi = o.qkv->vt_hi; T.vt_lo = o.qkv->vt_lo;
+    }
     const KSeg& S = P.seg[0];
     T.taps = S.taps; T.Cin = S.C0 + S.C1; T.Cout = P.Cout; T.B = B; T.geo = P.geo;
     T.bias = P.bias; T.resid = P.resid; T.resid_mode = P.resid_mode; T.out = P.out;
     const int M = B * P.geo.L;
     const int mtiles = P.geo.L > 128 ? M / 128 : (B + (128 / P.geo.L) - 1) / (128 / P.geo.L);
     int bn = 64;
-    if (P.Cout % 128 == 0 && mtiles * (P.Cout / 128) >= h->num_sms) bn = 128;
+    if (P.Cout % 128 == 0 && mtiles * (P.Cout / 128) >= 64) bn = 128;   // fewer smem bytes per MMA once the SMs are covered
     T.bn = bn;
-    tc_operand(name, S, P.geo, T.tmA_hi, T.tmA_lo, norm0);
+    {
+      const SplitBuf a0 = o.pre0 ? *o.pre0 : emit_apply(name, S, P.geo, norm0, o.raw_out);
+      make_A_maps(a0, T.Cin, S.taps, P.geo, T.tmA_hi, T.tmA_lo);
+    }
     auto wmaps = [&](const KSeg& K, CUtensorMap& whi, CUtensorMap& wlo) {
       const auto& pr = h->tc_w.at(K.w);
       const int C = K.C0 + K.C1;
@@ -470,14 +490,15 @@ struct Builder {
     if (P.nsegs == 2) {
       const KSeg& X = P.seg[1];
       T.Cin2 = X.C0 + X.C1;
-      tc_operand(name + ".skip", X, P.geo, T.tmA2_hi, T.tmA2_lo, norm1);
+      const SplitBuf a1 = o.pre1 ? *o.pre1 : emit_apply(name + ".skip", X, P.geo, norm1, nullptr);
+      make_A_maps(a1, T.Cin2, 1, P.geo, T.tmA2_hi, T.tmA2_lo);
       wmaps(X, T.tmW2_hi, T.tmW2_lo);
       Ktot += T.Cin2;
     }
     const int iters = T.taps * (T.Cin / 64) + T.Cin2 / 64;
     const int base = mtiles * (P.Cout / bn);
     int ks = 1;
-    if (base < 64 && iters >= 32 && ((h->tc_mask >> 5) & 1)) {
+    if (base < 64 && iters >= 32 && ((h->tc_mask >> 5) & 1) && !o.qkv) {
       ks = std::min(iters / 4, (h->num_sms + base - 1) / base);
       ks = std::min(ks, 32);
       while (ks > 1 && (ks - 1) * ((iters + ks - 1) / ks) >= iters) --ks;
@@ -491,10 +512,12 @@ struct Builder {
     pl->ops.push_back(op);
   }
 
+  bool fuse_launches() const { return h->cfg.kernel_path != 1 && ((h->tc_mask >> 9) & 1); }
   void conv(const std::string& name, ConvParams P, int norm0 = -1, int norm1 = -1, Tensor* out_t = nullptr,
-            int phase = 1, bool out_is_ctx = false) {
+            int phase = 1, bool out_is_ctx = false, const TcOpts& opts = TcOpts()) {
     P.B = B;
-    if (phase == 1 && !out_is_ctx && tc_ok(P)) { conv_tc(name, P, norm0, norm1, out_t); return; }
+    if (phase == 1 && !out_is_ctx && tc_ok(P)) { conv_tc(name, P, norm0, norm1, out_t, opts); return; }
+    if (opts.pre0 || opts.pre1 || opts.qkv) throw MtvError("internal: tensor-core-only options on a CUDA-core op: " + name);
     const int nid[2] = {norm0, norm1};
     for (int s = 0; s < P.nsegs; ++s)
       if (nid[s] >= 0) {
@@ -528,6 +551,7 @@ struct Builder {
     if (cin != r.cin) throw MtvError("internal: channel mismatch at " + p);
     const int n1 = gn(p + ".in_layers.0", x0, x1, false, h->W(p + ".in_layers.0.weight"), h->W(p + ".in_layers.0.bias"), -1);
     Tensor hmid = T(r.cout, level_out);
+    SplitBuf skip_raw; bool have_raw = false;
     {
       ConvParams P{}; P.nsegs = 1; P.geo = geo(level_out); P.Cout = r.cout;
       KSeg& S = P.seg[0];
@@ -535,7 +559,15 @@ struct Builder {
       S.silu = 1; S.resample = r.updown; S.taps = 9;
       S.w = h->W(p + ".in_layers.2.weight");
       P.bias = h->W(p + ".in_layers.2.bias"); P.out = hmid.p;
-      conv(p + ".in_layers.2", P, n1, -1, &hmid);
+      // when both convs run on the tensor cores, conv1's apply kernel also emits the raw split of x that
+      // conv2's fused 1x1 skip segment consumes (one launch instead of two)
+      if (r.cin != r.cout && fuse_launches() && tc_ok_pb(P)) {
+        ConvParams P2{}; P2.nsegs = 2; P2.geo = geo(level_out); P2.Cout = r.cout;
+        P2.seg[0].C0 = r.cout; P2.seg[0].taps = 9; P2.seg[0].w = h->W(p + ".out_layers.3.weight");
+        P2.seg[1].C0 = x0.C; P2.seg[1].C1 = x1 ? x1->C : 0; P2.seg[1].taps = 1; P2.seg[1].w = h->W(p + ".skip_connection.weight");
+        if (tc_ok_pb(P2)) { TcOpts o; o.raw_out = &skip_raw; conv(p + ".in_layers.2", P, n1, -1, &hmid, 1, false, o); have_raw = true; }
+      }
+      if (!have_raw) conv(p + ".in_layers.2", P, n1, -1, &hmid);
     }
     const int n2 = gn(p + ".out_layers.0", hmid, nullptr, false, h->W(p + ".out_layers.0.weight"),
                       h->W(p + ".out_layers.0.bias"), r.film_off);
@@ -556,7 +588,8 @@ struct Builder {
         P.resid = x0.p; P.resid_mode = r.updown;
       }
       P.out = out.p;
-      conv(p + ".out_layers.3", P, n2, -1, &out);
+      TcOpts o; if (have_raw) o.pre1 = &skip_raw;
+      conv(p + ".out_layers.3", P, n2, -1, &out, 1, false, o);
     }
     return out;
   }
@@ -565,65 +598,94 @@ struct Builder {
     const std::string& p = a.name;
     const int C = a.C, heads = h->cfg.num_heads;
     if (x.C != C) throw MtvError("internal: channel mismatch at " + p);
+    const int D = C / heads;
+    if (C % heads || !(D == 16 || D == 32 || D == 64 || D == 128))
+      throw MtvError("attention head dim must be 16/32/64/128 at " + p);
+    const int L = geo(level).L;
     const int n = gn(p + ".norm", x, nullptr, a.joint, h->W(p + ".norm.weight"), h->W(p + ".norm.bias"), -1);
-    Tensor qkv = T(3 * C, level);
-    {
-      ConvParams P{}; P.nsegs = 1; P.geo = geo(level); P.Cout = 3 * C;
-      KSeg& S = P.seg[0];
-      S.src0 = x.p; S.C0 = C; S.silu = 0; S.taps = 1;
-      S.w = h->W(p + ".qkv.weight"); P.bias = h->W(p + ".qkv.bias"); P.out = qkv.p;
-      conv(p + ".qkv", P, n);
+
+    ConvParams Pq{}; Pq.nsegs = 1; Pq.geo = geo(level); Pq.Cout = 3 * C;
+    { KSeg& S = Pq.seg[0]; S.src0 = x.p; S.C0 = C; S.silu = 0; S.taps = 1; S.w = h->W(p + ".qkv.weight"); }
+    Pq.bias = h->W(p + ".qkv.bias");
+    ConvParams Pp{}; Pp.nsegs = 1; Pp.geo = geo(level); Pp.Cout = C;
+    { KSeg& S = Pp.seg[0]; S.C0 = C; S.taps = 1; S.w = h->W(p + ".proj_out.weight"); }
+    Pp.bias = h->W(p + ".proj_out.bias"); Pp.resid = x.p; Pp.resid_mode = RS_NONE;
+
+    const bool tc_attn = h->cfg.kernel_path != 1 && ((h->tc_mask >> 6) & 1) && (D == 16 || D == 32 || D == 64);
+    const bool fuse = tc_attn && fuse_launches() && tc_ok_pb(Pq) && tc_ok_pb(Pp);
+
+    AttnParams A{}; A.B = B; A.L = L; A.C = C; A.heads = heads;
+    set_segs(level, a.joint, A.nseg, A.seg_off);
+    double pairs = 0;
+    for (int i = 0; i < A.nseg; ++i) { const double l = A.seg_off[i + 1] - A.seg_off[i]; pairs += l * l; }
+
+    QkvSplitParams Q{};
+    if (tc_attn) {
+      const size_t bytes = (size_t)B * L * C * 2;
+      Q.B = B; Q.L = L; Q.C = C; Q.heads = heads;
+      Q.q_hi = dalloc(bytes); Q.q_lo = dalloc(bytes); Q.k_hi = dalloc(bytes); Q.k_lo = dalloc(bytes);
+      Q.vt_hi = dalloc(bytes); Q.vt_lo = dalloc(bytes);
     }
-    Tensor att = T(C, level);
-    {
-      AttnParams P{}; P.qkv = qkv.p; P.out = att.p; P.B = B; P.L = geo(level).L; P.C = C; P.heads = heads;
-      set_segs(level, a.joint, P.nseg, P.seg_off);
-      const int D = C / heads;
-      if (C % heads || !(D == 16 || D == 32 || D == 64 || D == 128))
-        throw MtvError("attention head dim must be 16/32/64/128 at " + p);
-      double pairs = 0;
-      for (int i = 0; i < P.nseg; ++i) { const double l = P.seg_off[i + 1] - P.seg_off[i]; pairs += l * l; }
-      const bool tc_attn = h->cfg.kernel_path != 1 && ((h->tc_mask >> 6) & 1) && (D == 16 || D == 32 || D == 64);
+    // ---- qkv projection
+    Tensor qkv;
+    if (fuse) {             // the GEMM epilogue writes Q / K / V^T directly; no fp32 qkv tensor
+      TcOpts o; o.qkv = &Q;
+      conv(p + ".qkv", Pq, n, -1, nullptr, 1, false, o);
+    } else {
+      qkv = T(3 * C, level);
+      Pq.out = qkv.p;
+      conv(p + ".qkv", Pq, n);
       if (tc_attn) {
-        const size_t bytes = (size_t)B * P.L * C * 2;
-        QkvSplitParams Q{}; Q.qkv = qkv.p; Q.B = B; Q.L = P.L; Q.C = C; Q.heads = heads;
-        Q.q_hi = dalloc(bytes); Q.q_lo = dalloc(bytes); Q.k_hi = dalloc(bytes); Q.k_lo = dalloc(bytes);
-        Q.vt_hi = dalloc(bytes); Q.vt_lo = dalloc(bytes);
-        { Op op; op.name = "qkv_split:" + p; op.bytes = (double)B * P.L * C * 24;
-          op.fn = [Q](cudaStream_t s) { return launch_qkv_split(Q, s); }; pl->ops.push_back(op); }
-        AttnTcParams T{}; T.out = att.p; T.B = B; T.L = P.L; T.C = C; T.heads = heads; T.nseg = P.nseg;
-        for (int i = 0; i < 4; ++i) T.seg_off[i] = P.seg_off[i];
-        const uint64_t rows = (uint64_t)B * heads * P.L;
-        {
-          const uint64_t dims[2] = {(uint64_t)D, rows}; const uint64_t str[1] = {(uint64_t)D * 2};
-          const uint32_t bq[2] = {(uint32_t)D, 128}, bk[2] = {(uint32_t)D, 64};
-          T.tmQ_hi = make_tmap_bf16(Q.q_hi, 2, dims, str, bq, 2 * D); T.tmQ_lo = make_tmap_bf16(Q.q_lo, 2, dims, str, bq, 2 * D);
-          T.tmK_hi = make_tmap_bf16(Q.k_hi, 2, dims, str, bk, 2 * D); T.tmK_lo = make_tmap_bf16(Q.k_lo, 2, dims, str, bk, 2 * D);
-        }
-        {
-          const uint64_t dims[2] = {(uint64_t)P.L, (uint64_t)B * heads * D}; const uint64_t str[1] = {(uint64_t)P.L * 2};
-          const uint32_t bv[2] = {64, (uint32_t)D};
-          T.tmV_hi = make_tmap_bf16(Q.vt_hi, 2, dims, str, bv, 128); T.tmV_lo = make_tmap_bf16(Q.vt_lo, 2, dims, str, bv, 128);
-        }
-        Op op; op.name = "attn_tc:" + p;
-        op.flops = 4.0 * B * heads * pairs * D; op.bytes = 4.0 * B * P.L * 4 * C;
-        op.fn = [T](cudaStream_t s) { return launch_attn_tc(T, s); };
-        pl->ops.push_back(op);
-      } else {
-        Op op; op.name = "attn:" + p;
-        op.flops = 4.0 * B * heads * pairs * D;
-        op.bytes = 4.0 * B * P.L * 4 * C;
-        op.fn = [P](cudaStream_t s) { return launch_attn_simt(P, s); };
-        pl->ops.push_back(op);
+        Q.qkv = qkv.p;
+        Op op; op.name = "qkv_split:" + p; op.bytes = (double)B * L * C * 24;
+        op.fn = [Q](cudaStream_t s) { return launch_qkv_split(Q, s); }; pl->ops.push_back(op);
       }
     }
-    Tensor out = T(C, level);
-    {
-      ConvParams P{}; P.nsegs = 1; P.geo = geo(level); P.Cout = C;
-      KSeg& S = P.seg[0];
-      S.src0 = att.p; S.C0 = C; S.taps = 1; S.w = h->W(p + ".proj_out.weight");
-      P.bias = h->W(p + ".proj_out.bias"); P.resid = x.p; P.resid_mode = RS_NONE; P.out = out.p;
-      conv(p + ".proj_out", P, -1, -1, &out);
+    // ---- attention core
+    Tensor att; SplitBuf att_split;
+    if (tc_attn) {
+      AttnTcParams T{}; T.B = B; T.L = L; T.C = C; T.heads = heads; T.nseg = A.nseg;
+      for (int i = 0; i < 4; ++i) T.seg_off[i] = A.seg_off[i];
+      if (fuse) {
+        const size_t bytes = (size_t)B * L * C * 2;
+        att_split.hi = dalloc(bytes); att_split.lo = dalloc(bytes);
+        T.out_hi = att_split.hi; T.out_lo = att_split.lo;
+      } else {
+        att = this->T(C, level); T.out = att.p;
+      }
+      const uint64_t rows = (uint64_t)B * heads * L;
+      {
+        const uint64_t dims[2] = {(uint64_t)D, rows}; const uint64_t str[1] = {(uint64_t)D * 2};
+        const uint32_t bq[2] = {(uint32_t)D, 128}, bk[2] = {(uint32_t)D, 64};
+        T.tmQ_hi = make_tmap_bf16(Q.q_hi, 2, dims, str, bq, 2 * D); T.tmQ_lo = make_tmap_bf16(Q.q_lo, 2, dims, str, bq, 2 * D);
+        T.tmK_hi = make_tmap_bf16(Q.k_hi, 2, dims, str, bk, 2 * D); T.tmK_lo = make_tmap_bf16(Q.k_lo, 2, dims, str, bk, 2 * D);
+      }
+      {
+        const uint64_t dims[2] = {(uint64_t)L, (uint64_t)B * heads * D}; const uint64_t str[1] = {(uint64_t)L * 2};
+        const uint32_t bv[2] = {64, (uint32_t)D};
+        T.tmV_hi = make_tmap_bf16(Q.vt_hi, 2, dims, str, bv, 128); T.tmV_lo = make_tmap_bf16(Q.vt_lo, 2, dims, str, bv, 128);
+      }
+      Op op; op.name = "attn_tc:" + p;
+      op.flops = 4.0 * B * heads * pairs * D; op.bytes = 4.0 * B * L * 4 * C;
+      op.fn = [T](cudaStream_t s) { return launch_attn_tc(T, s); };
+      pl->ops.push_back(op);
+    } else {
+      att = this->T(C, level);
+      A.qkv = qkv.p; A.out = att.p;
+      Op op; op.name = "attn:" + p;
+      op.flops = 4.0 * B * heads * pairs * D; op.bytes = 4.0 * B * L * 4 * C;
+      op.fn = [A](cudaStream_t s) { return launch_attn_simt(A, s); };
+      pl->ops.push_back(op);
+    }
+    // ---- output projection + residual
+    Tensor out = this->T(C, level);
+    Pp.out = out.p;
+    if (fuse) {
+      TcOpts o; o.pre0 = &att_split;
+      conv(p + ".proj_out", Pp, -1, -1, &out, 1, false, o);
+    } else {
+      Pp.seg[0].src0 = att.p;
+      conv(p + ".proj_out", Pp, -1, -1, &out);
     }
     return out;
   }
@@ -838,6 +900,7 @@ int mtv_create(const MtvConfig* cfg, MtvHandle* out) {
     const char* ng = getenv("MTV_NO_GRAPH");
     h->use_graph = !(ng && ng[0] == '1');
     if (const char* tm = getenv("MTV_TC_MASK")) h->tc_mask = (int)strtol(tm, nullptr, 0);
+    { const char* np = getenv("MTV_NO_PDL"); g_mtv_use_pdl = (np && np[0] == '1') ? 0 : 1; }
     register_weights(h.get());
     *out = h.release();
   });

@@ -19,6 +19,7 @@ struct ApplyParams {
   int chunk_tokens;                                    // tokens of one plane per CTA
   int B; Geo geo;                                      // OUTPUT geometry
   void* hi; void* lo;                                  // __nv_bfloat16 [B][L][C0+C1]
+  void* raw_hi; void* raw_lo;                          // optional: split of the UN-normalised (but resampled) input as well
 };
 
 // D[B*L][Cout] = sum_tap A_tap[B*L][Cin] * W[tap][Cout][Cin]^T   (+bias, +residual)
@@ -37,6 +38,10 @@ struct TcConvParams {
   const float* bias; const float* resid; int resid_mode;
   float* out; float* partial; int ksplit;
   double* csum;                       // optional [B][3][Cout][2]: per-channel sums of `out` for the next GroupNorm
+  // qkv mode (qkv_heads > 0): instead of fp32 `out`, the epilogue writes the attention operands directly —
+  // split-bf16 Q (pre-scaled by log2(e)/sqrt(D)) and K as [B*H][L][D], V^T as [B*H][D][L]  (see k_qkv_split)
+  int qkv_heads;
+  void* q_hi; void* q_lo; void* k_hi; void* k_lo; void* vt_hi; void* vt_lo;
 };
 
 // qkv fp32 [B][L][3C] -> split-bf16 Q (pre-scaled), K [B*H][L][D] and V^T [B*H][D][L]
@@ -49,7 +54,8 @@ struct AttnTcParams {
   CUtensorMap tmQ_hi, tmQ_lo;     // (D, B*H*L) box (D, 128)
   CUtensorMap tmK_hi, tmK_lo;     // (D, B*H*L) box (D, 64)
   CUtensorMap tmV_hi, tmV_lo;     // (L, B*H*D) box (64, D)
-  float* out;                     // [B][L][C]
+  float* out;                     // [B][L][C] fp32, or nullptr when out_hi / out_lo are given
+  void* out_hi; void* out_lo;     // optional split-bf16 [B][L][C]: the A operand of the proj_out GEMM
   int B, L, C, heads;
   int nseg; int seg_off[4];
 };

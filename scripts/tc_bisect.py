@@ -2,7 +2,8 @@
 Runs the forward with MTV_TC_MASK restricted to one class at a time and prints the error of
 every stage against the all-CUDA-core run.  (bits: 0-2 conv3x3 at level 0/1/2, 3 = 1x1 GEMMs,
 4 = conv3x3 with fused skip 1x1, 5 = allow split-K, 6 = tcgen05 attention, 7 = tensor-core tiles at the
-32-token level, 8 = GroupNorm statistics fused into the tap-GEMM epilogue / apply prologue)"""
+32-token level, 8 = GroupNorm statistics fused into the tap-GEMM epilogue / apply prologue, 9 = launch fusions:
+qkv split in the GEMM epilogue, attention writes the proj operand, shared skip-operand apply)"""
 import os
 import sys
 
@@ -44,13 +45,15 @@ def main():
     taps_ref = {k: ref.diffusion_model.debug_read(k, B, C, L) for k, C, L in stages(cfg)}
     cases = (("conv L0", 1), ("conv L1", 2), ("conv L2", 4), ("gemm 1x1", 8), ("conv+skip", 16), ("conv L2 + splitK", 4 | 32))
     if "new" in sys.argv:   # the classes verified so far as a base, plus one newer feature at a time
-        cases = (("base 0x3f", 0x3f), ("+tc attention", 0x3f | 0x40), ("+level-3 tiles", 0x3f | 0x80),
-                 ("+fused groupnorm", 0x3f | 0x100), ("+l3 +gn", 0x3f | 0x180), ("all", 0x1ff))
+        cases = (("verified 0x1ff, no PDL", 0x1ff), ("verified 0x1ff + PDL", 0x1ff), ("+fused launches, no PDL", 0x3ff),
+                 ("all (0x3ff + PDL)", 0x3ff))
     for name, mask in cases:
+        os.environ["MTV_NO_PDL"] = "1" if "no PDL" in name else "0"
         try:
             m = make(cfg, 0, mask)
             with torch.no_grad():
-                e = m(x, c, ic, t)
+                for _ in range(3):          # eager, graph capture, graph replay
+                    e = m(x, c, ic, t)
             torch.cuda.synchronize()
             errs = []
             for k, C, L in stages(cfg):
