@@ -168,7 +168,6 @@ struct AttnSmem {
 template <int D>
 __global__ void __launch_bounds__(AT_THREADS, 1) k_attn_tc(const __grid_constant__ AttnTcParams P) {
   using SM = AttnSmem<D>;
-  MTV_PDL_TRIGGER();
   constexpr uint32_t IDESC_S = a_idesc(AT_BQ, AT_BKV);
   constexpr uint32_t IDESC_O = a_idesc(AT_BQ, D);
   constexpr int TMEM_COLS = 128;                           // S: cols [0,64), O block: cols [64, 64+D)
@@ -234,6 +233,8 @@ __global__ void __launch_bounds__(AT_THREADS, 1) k_attn_tc(const __grid_constant
         if (++stage == AT_NS) { stage = 0; phase ^= 1u; }
       }
     }
+    a_mbar_wait(&bar_o_full, (uint32_t)((nblk - 1) & 1));   // all threads trigger when only the epilogue remains
+    MTV_PDL_TRIGGER();
   } else if (warp == 1) {
     // =============================== MMA issuer =================================
     if (lane == 0) {
@@ -279,6 +280,8 @@ __global__ void __launch_bounds__(AT_THREADS, 1) k_attn_tc(const __grid_constant
         stage = nstage; phase = nphase;
       }
     }
+    a_mbar_wait(&bar_o_full, (uint32_t)((nblk - 1) & 1));
+    MTV_PDL_TRIGGER();
   } else {
     // =============================== softmax / epilogue ==========================
     const int qq = warp & 3;
@@ -358,6 +361,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) k_attn_tc(const __grid_constant
       a_mbar_arrive(&bar_p_full);
     }
     a_mbar_wait(&bar_o_full, (uint32_t)((nblk - 1) & 1));
+    MTV_PDL_TRIGGER();
     a_fence_after();
     fold_O();
     const int q = q0 + row;

@@ -67,7 +67,6 @@ __device__ __forceinline__ void store_out(const ConvParams& P, int b, int tok, i
 template <int BM, int BN, int TM, int TN>
 __global__ void __launch_bounds__((BM / TM) * (BN / TN))
 k_conv_simt(const __grid_constant__ ConvParams P) {
-  MTV_PDL_TRIGGER();
   MTV_PDL_WAIT();
   constexpr int NT = (BM / TM) * (BN / TN);
   constexpr int BK = 16;
@@ -215,6 +214,7 @@ k_conv_simt(const __grid_constant__ ConvParams P) {
     __syncthreads();
   }
 
+  MTV_PDL_TRIGGER();
   // epilogue
 #pragma unroll
   for (int i = 0; i < TM; ++i) {
