@@ -344,21 +344,29 @@ __host__ __device__ constexpr int tc_smem_bytes(int BN) { return tc_stages(BN) *
 struct TcTile {
   bool small; int spt; int b0; int tok0;
   int nxy, npl;
+  int sh_xy, sh_pl, sh_res;     // log2 of nxy, npl, res (all powers of two: res = 32 >> level, t = 16 >> level)
 };
 __device__ __forceinline__ TcTile tc_tile(const Geo& g, int tile) {
   TcTile t;
   t.small = g.L <= TC_BM; t.nxy = g.res * g.res; t.npl = g.t * g.res;
+  t.sh_xy = 31 - __clz(t.nxy); t.sh_pl = 31 - __clz(t.npl); t.sh_res = 31 - __clz(g.res);
   if (t.small) { t.spt = TC_BM / g.L; t.b0 = tile * t.spt; t.tok0 = 0; }
   else { const int tps = g.L / TC_BM; t.spt = 1; t.b0 = tile / tps; t.tok0 = (tile - t.b0 * tps) * TC_BM; }
   return t;
 }
-// tile row -> (sample, token within the sample)
+// tile row -> (sample, token within the sample); division-free (hot in the epilogue)
 __device__ __forceinline__ void tc_row_map(const TcTile& t, int row, int& b, int& tok) {
   if (!t.small) { b = t.b0; tok = t.tok0 + row; return; }
-  const int e1 = t.spt * t.nxy, e2 = e1 + t.spt * t.npl;
-  if (row < e1) { const int s = row / t.nxy; b = t.b0 + s; tok = row - s * t.nxy; }
-  else if (row < e2) { const int r = row - e1; const int s = r / t.npl; b = t.b0 + s; tok = t.nxy + (r - s * t.npl); }
-  else { const int r = row - e2; const int s = r / t.npl; b = t.b0 + s; tok = t.nxy + t.npl + (r - s * t.npl); }
+  const int e1 = t.spt << t.sh_xy, e2 = e1 + (t.spt << t.sh_pl);
+  if (row < e1) { const int s = row >> t.sh_xy; b = t.b0 + s; tok = row & (t.nxy - 1); }
+  else if (row < e2) { const int r = row - e1; b = t.b0 + (r >> t.sh_pl); tok = t.nxy + (r & (t.npl - 1)); }
+  else { const int r = row - e2; b = t.b0 + (r >> t.sh_pl); tok = t.nxy + t.npl + (r & (t.npl - 1)); }
+}
+// token -> (plane, y, x) with shifts
+__device__ __forceinline__ void tc_decode_fast(const TcTile& t, int tok, int& p, int& y, int& x) {
+  int r = tok; p = 0;
+  if (tok >= t.nxy) { r = tok - t.nxy; p = 1; if (r >= t.npl) { r -= t.npl; p = 2; } }
+  y = r >> t.sh_res; x = r & ((1 << t.sh_res) - 1);
 }
 
 // one 128-row A operand tile (hi and lo) for K-chunk c0 of tap `tap`
@@ -613,7 +621,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
       __syncwarp();
       float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
       if (P.bias && P.ksplit <= 1) bv = __ldg(reinterpret_cast<const float4*>(P.bias + n + cc));
+      // qkv mode: which of q / k / v (and which head) this lane's 4 columns belong to — row independent
+      int qk_kind = 2, qk_hd = 0, qk_d0 = 0, qk_D = 1; float qk_scale = 1.0f;
+      if (P.qkv_heads) {
+        qk_D = P.Cout / (3 * P.qkv_heads);
+        const int nn = n + cc;
+        qk_hd = nn / (3 * qk_D);
+        const int rq = nn - qk_hd * 3 * qk_D;
+        qk_kind = rq / qk_D; qk_d0 = rq - qk_kind * qk_D;
+        if (qk_kind == 0) qk_scale = 1.4426950408889634f * rsqrtf((float)qk_D);
+      }
       float cs[4] = {0.f, 0.f, 0.f, 0.f}, cq[4] = {0.f, 0.f, 0.f, 0.f};
+      // same-geometry residual rows are fetched up front (8 independent 16-byte loads in flight per lane)
+      const bool res_pre = P.resid && P.resid_mode == RS_NONE && P.ksplit <= 1;
+      float4 rres[8];
+      if (res_pre) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          int b, tok; tc_row_map(T, q * 32 + 4 * i + sub, b, tok);
+          rres[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (b < P.B) rres[i] = __ldg(reinterpret_cast<const float4*>(P.resid + ((size_t)b * g.L + tok) * P.Cout + n + cc));
+        }
+      }
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int rr = 4 * i + sub;                                  // row within this warp's 32
@@ -628,10 +657,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
             v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
             if (P.resid) {
               if (P.resid_mode == RS_NONE) {
-                const float4 rv = __ldg(reinterpret_cast<const float4*>(P.resid + m * P.Cout + n + cc));
+                const float4 rv = rres[i];
                 v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
               } else {
-                int p, y, x; tc_decode_tok(g, tok, p, y, x);
+                int p, y, x; tc_decode_fast(T, tok, p, y, x);
                 if (P.resid_mode == RS_UP2) {
                   const Geo gs = geo_down(g);
                   const int ts = tc_plane_off(gs, p) + (y >> 1) * gs.res + (x >> 1);
@@ -652,15 +681,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
             }
             if (P.qkv_heads) {
               // q / k columns: 4 consecutive channels of one head, stored as split bf16 [B*H][L][D]
-              const int Dh = P.Cout / (3 * P.qkv_heads);
-              const int nn = n + cc;
-              const int hd = nn / (3 * Dh), rq = nn - hd * 3 * Dh;
-              const int kind = rq / Dh, d0 = rq - kind * Dh;
-              if (kind < 2) {
-                const float qs = kind == 0 ? 1.4426950408889634f * rsqrtf((float)Dh) : 1.0f;
-                const size_t o = (((size_t)b * P.qkv_heads + hd) * g.L + tok) * Dh + d0;
-                tc_store_split(make_float4(v.x * qs, v.y * qs, v.z * qs, v.w * qs), kind == 0 ? P.q_hi : P.k_hi,
-                               kind == 0 ? P.q_lo : P.k_lo, o);
+              if (qk_kind < 2) {
+                const size_t o = (((size_t)b * P.qkv_heads + qk_hd) * g.L + tok) * qk_D + qk_d0;
+                tc_store_split(make_float4(v.x * qk_scale, v.y * qk_scale, v.z * qk_scale, v.w * qk_scale),
+                               qk_kind == 0 ? P.q_hi : P.k_hi, qk_kind == 0 ? P.q_lo : P.k_lo, o);
               }
             } else {
               *reinterpret_cast<float4*>(P.out + m * P.Cout + n + cc) = v;
@@ -678,7 +702,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
           }
           int b8, tok8; tc_row_map(T, q * 32 + 8 * (i >> 1), b8, tok8);
           if (lane < 8 && b8 < P.B) {
-            int p8, y8, x8; tc_decode_tok(g, tok8, p8, y8, x8);
+            const int p8 = tok8 < T.nxy ? 0 : (tok8 - T.nxy < T.npl ? 1 : 2);
             double* dst = P.csum + (((size_t)b8 * 3 + p8) * P.Cout + n + cc) * 2;
 #pragma unroll
             for (int k = 0; k < 4; ++k) { atomicAdd(dst + 2 * k, (double)cs[k]); atomicAdd(dst + 2 * k + 1, (double)cq[k]); }
