@@ -444,6 +444,33 @@ __device__ __forceinline__ void tc_csum_chunk(float (&v)[32], bool live, int lan
   }
 }
 
+// Same, over all 32 rows of the warp (valid when they share one (sample, plane)): after five exchange
+// steps lane l holds column l -> 2 atomics per lane instead of 8, and 4x fewer same-address atomics.
+__device__ __forceinline__ void tc_csum_chunk32(float (&v)[32], bool live, int lane, double* csum_bp) {
+  float q[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) { if (!live) v[i] = 0.f; q[i] = v[i] * v[i]; }
+#pragma unroll
+  for (int step = 0; step < 5; ++step) {
+    const int off = 16 >> step, hn = 16 >> step;
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      if (i < hn) {
+        const float sv = up ? v[i] : v[i + hn], sq = up ? q[i] : q[i + hn];
+        const float rv = __shfl_xor_sync(0xffffffffu, sv, off), rq = __shfl_xor_sync(0xffffffffu, sq, off);
+        v[i] = (up ? v[i + hn] : v[i]) + rv;
+        q[i] = (up ? q[i + hn] : q[i]) + rq;
+      }
+    }
+  }
+  // the whole warp shares liveness here (uniform (sample, plane)); lane l owns column l
+  if (__any_sync(0xffffffffu, live)) {
+    atomicAdd(csum_bp + 2 * lane, (double)v[0]);
+    atomicAdd(csum_bp + 2 * lane + 1, (double)q[0]);
+  }
+}
+
 template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant__ TcConvParams P) {
   constexpr int NS = tc_stages(BN);
@@ -570,146 +597,131 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
     MTV_PDL_TRIGGER();
   } else {
     // =============================== epilogue ===================================
-    // TMEM -> registers (thread == tile row) -> per-warp smem transpose -> 8 lanes per row, so every
-    // global access of the epilogue (residual load, output store) is a full 128-byte row segment
-    // instead of 32 scattered 16-byte pieces.  The staging area is pipeline stage 0, free once the
-    // accumulator barrier has fired.
     const int q = warp & 3;                       // TMEM lane quarter this warp may read
-    MTV_PDL_WAIT();                               // residual / statistics buffers belong to earlier kernels
+    const int row = q * 32 + lane;                // row of the tile
+    int b, tok; tc_row_map(T, row, b, tok);
+    const bool live = b < P.B;
+    const size_t m = (size_t)b * g.L + tok;
+    MTV_PDL_WAIT();                                 // residual / statistics buffers belong to earlier kernels
+    // the residual and bias of the first 32-column chunk are fetched while the MMAs still run
+    const bool pre_res = live && P.resid && P.resid_mode == RS_NONE && P.ksplit <= 1;
+    float4 rpre[8];
+    if (pre_res) {
+      const float4* rp4 = reinterpret_cast<const float4*>(P.resid + m * P.Cout + n0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) rpre[j] = __ldg(rp4 + j);
+    }
     mbar_wait(&bar_acc, 0);
     MTV_PDL_TRIGGER();
     if (dbg && threadIdx.x == 64) s_stamp[5] = clock64();            // accumulator complete
     tc_fence_after();
-    float* stg = reinterpret_cast<float*>(smem_raw + (smem0 - smem_u32(smem_raw))) + q * (32 * 36);
-    const int sub = lane >> 3, cc = (lane & 7) * 4;                  // transposed role: row-in-group-of-4, column quad
-    const size_t Mrows = (size_t)P.B * g.L;
+    int p = 0, y = 0, x = 0;
+    if ((P.resid && P.resid_mode != RS_NONE) || P.csum) tc_decode_fast(T, tok, p, y, x);
+    const int pl_stat = p;
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       uint32_t r[32];
       __syncwarp();
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
       const int n = n0 + c0;
-      if (P.qkv_heads) {
-        // V^T columns go out straight from the row-per-lane registers (32 consecutive tokens per channel
-        // = one 64-byte segment); q / k columns take the transposed path below
-        const int Dh = P.Cout / (3 * P.qkv_heads);
-        int b, tok; tc_row_map(T, q * 32 + lane, b, tok);
-        if (b < P.B) {
+      float4 rnext[8];
+      const bool have_next = pre_res && (c0 + 32 < BN);
+      if (have_next) {
+        const float4* rp4 = reinterpret_cast<const float4*>(P.resid + m * P.Cout + n + 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) rnext[j] = __ldg(rp4 + j);
+      }
+      if (!live) {
+        // rows of samples beyond the batch (partial last tile of a small level): nothing to store
+      } else if (P.ksplit > 1) {
+        float* dst = P.partial + ((size_t)blockIdx.z * ((size_t)P.B * g.L) + m) * P.Cout + n;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                            __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+      } else {
+        float* dst = P.out + m * P.Cout + n;
+        float fv[32];
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+          if (P.bias) {
+            const float4 bv = __ldg(reinterpret_cast<const float4*>(P.bias + n + j));
+            v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+          }
+          if (P.resid) {
+            if (P.resid_mode == RS_NONE) {
+              const float4 rv = rpre[j >> 2];
+              v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
+            } else if (P.resid_mode == RS_UP2) {
+              const Geo gs = geo_down(g);
+              const int ts = tc_plane_off(gs, p) + (y >> 1) * gs.res + (x >> 1);
+              const float4 rv = __ldg(reinterpret_cast<const float4*>(P.resid + ((size_t)b * gs.L + ts) * P.Cout + n + j));
+              v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
+            } else {
+              const Geo gs = geo_up(g);
+              const int t0 = tc_plane_off(gs, p) + (2 * y) * gs.res + 2 * x;
+              const float* rp = P.resid + ((size_t)b * gs.L + t0) * P.Cout + n + j;
+              const float4 r0 = __ldg(reinterpret_cast<const float4*>(rp));
+              const float4 r1 = __ldg(reinterpret_cast<const float4*>(rp + P.Cout));
+              const float4 r2 = __ldg(reinterpret_cast<const float4*>(rp + (size_t)gs.res * P.Cout));
+              const float4 r3 = __ldg(reinterpret_cast<const float4*>(rp + (size_t)(gs.res + 1) * P.Cout));
+              v.x += 0.25f * (r0.x + r1.x + r2.x + r3.x); v.y += 0.25f * (r0.y + r1.y + r2.y + r3.y);
+              v.z += 0.25f * (r0.z + r1.z + r2.z + r3.z); v.w += 0.25f * (r0.w + r1.w + r2.w + r3.w);
+            }
+          }
+          if (!P.qkv_heads) *reinterpret_cast<float4*>(dst + j) = v;
+          fv[j] = v.x; fv[j + 1] = v.y; fv[j + 2] = v.z; fv[j + 3] = v.w;
+        }
+        if (P.qkv_heads) {
+          // channels are head-major [h: q(D) k(D) v(D)] (unet.py:321); D >= 16, so every aligned run of 16
+          // channels is one of q / k / v of one head
+          const int Dh = P.Cout / (3 * P.qkv_heads);
+          const float qs = 1.4426950408889634f * rsqrtf((float)Dh);
 #pragma unroll
           for (int hf = 0; hf < 2; ++hf) {
             const int nn = n + hf * 16;
             const int hd = nn / (3 * Dh), rr = nn - hd * 3 * Dh;
-            if (rr / Dh == 2) {
-              const int d0 = rr - 2 * Dh;
-              const size_t bh = (size_t)b * P.qkv_heads + hd;
+            const int kind = rr / Dh, d0 = rr - kind * Dh;
+            const size_t bh = (size_t)b * P.qkv_heads + hd;
+            __align__(16) __nv_bfloat16 hh[16], ll[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float val = kind == 0 ? fv[hf * 16 + i] * qs : fv[hf * 16 + i];
+              hh[i] = __float2bfloat16_rn(val);
+              ll[i] = __float2bfloat16_rn(val - __bfloat162float(hh[i]));
+            }
+            if (kind < 2) {
+              __nv_bfloat16* ph = reinterpret_cast<__nv_bfloat16*>(kind == 0 ? P.q_hi : P.k_hi) + (bh * g.L + tok) * Dh + d0;
+              __nv_bfloat16* pw = reinterpret_cast<__nv_bfloat16*>(kind == 0 ? P.q_lo : P.k_lo) + (bh * g.L + tok) * Dh + d0;
+              reinterpret_cast<uint4*>(ph)[0] = reinterpret_cast<const uint4*>(hh)[0];
+              reinterpret_cast<uint4*>(ph)[1] = reinterpret_cast<const uint4*>(hh)[1];
+              reinterpret_cast<uint4*>(pw)[0] = reinterpret_cast<const uint4*>(ll)[0];
+              reinterpret_cast<uint4*>(pw)[1] = reinterpret_cast<const uint4*>(ll)[1];
+            } else {
               __nv_bfloat16* ph = reinterpret_cast<__nv_bfloat16*>(P.vt_hi) + (bh * Dh + d0) * g.L + tok;
               __nv_bfloat16* pw = reinterpret_cast<__nv_bfloat16*>(P.vt_lo) + (bh * Dh + d0) * g.L + tok;
 #pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const float val = __uint_as_float(r[hf * 16 + i]) + __ldg(P.bias + nn + i);
-                const __nv_bfloat16 hv = __float2bfloat16_rn(val);
-                ph[(size_t)i * g.L] = hv; pw[(size_t)i * g.L] = __float2bfloat16_rn(val - __bfloat162float(hv));
-              }
+              for (int i = 0; i < 16; ++i) { ph[(size_t)i * g.L] = hh[i]; pw[(size_t)i * g.L] = ll[i]; }
             }
           }
         }
-      }
+        if (P.csum) {   // uniform branch: statistics of the tensor just written, for the next GroupNorm
 #pragma unroll
-      for (int j = 0; j < 32; j += 4)
-        *reinterpret_cast<float4*>(stg + lane * 36 + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
-                                                                      __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
-      __syncwarp();
-      float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (P.bias && P.ksplit <= 1) bv = __ldg(reinterpret_cast<const float4*>(P.bias + n + cc));
-      // qkv mode: which of q / k / v (and which head) this lane's 4 columns belong to — row independent
-      int qk_kind = 2, qk_hd = 0, qk_d0 = 0, qk_D = 1; float qk_scale = 1.0f;
-      if (P.qkv_heads) {
-        qk_D = P.Cout / (3 * P.qkv_heads);
-        const int nn = n + cc;
-        qk_hd = nn / (3 * qk_D);
-        const int rq = nn - qk_hd * 3 * qk_D;
-        qk_kind = rq / qk_D; qk_d0 = rq - qk_kind * qk_D;
-        if (qk_kind == 0) qk_scale = 1.4426950408889634f * rsqrtf((float)qk_D);
-      }
-      float cs[4] = {0.f, 0.f, 0.f, 0.f}, cq[4] = {0.f, 0.f, 0.f, 0.f};
-      // same-geometry residual rows are fetched up front (8 independent 16-byte loads in flight per lane)
-      const bool res_pre = P.resid && P.resid_mode == RS_NONE && P.ksplit <= 1;
-      float4 rres[8];
-      if (res_pre) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          int b, tok; tc_row_map(T, q * 32 + 4 * i + sub, b, tok);
-          rres[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (b < P.B) rres[i] = __ldg(reinterpret_cast<const float4*>(P.resid + ((size_t)b * g.L + tok) * P.Cout + n + cc));
+          for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(fv[j]);
         }
       }
+      if (P.csum && P.ksplit <= 1) {
+        float fv[32];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int rr = 4 * i + sub;                                  // row within this warp's 32
-        int b, tok; tc_row_map(T, q * 32 + rr, b, tok);
-        const bool live = b < P.B;
-        float4 v = *reinterpret_cast<const float4*>(stg + rr * 36 + cc);
-        if (live) {
-          const size_t m = (size_t)b * g.L + tok;
-          if (P.ksplit > 1) {
-            *reinterpret_cast<float4*>(P.partial + ((size_t)blockIdx.z * Mrows + m) * P.Cout + n + cc) = v;
-          } else {
-            v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
-            if (P.resid) {
-              if (P.resid_mode == RS_NONE) {
-                const float4 rv = rres[i];
-                v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
-              } else {
-                int p, y, x; tc_decode_fast(T, tok, p, y, x);
-                if (P.resid_mode == RS_UP2) {
-                  const Geo gs = geo_down(g);
-                  const int ts = tc_plane_off(gs, p) + (y >> 1) * gs.res + (x >> 1);
-                  const float4 rv = __ldg(reinterpret_cast<const float4*>(P.resid + ((size_t)b * gs.L + ts) * P.Cout + n + cc));
-                  v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
-                } else {
-                  const Geo gs = geo_up(g);
-                  const int t0 = tc_plane_off(gs, p) + (2 * y) * gs.res + 2 * x;
-                  const float* rp = P.resid + ((size_t)b * gs.L + t0) * P.Cout + n + cc;
-                  const float4 r0 = __ldg(reinterpret_cast<const float4*>(rp));
-                  const float4 r1 = __ldg(reinterpret_cast<const float4*>(rp + P.Cout));
-                  const float4 r2 = __ldg(reinterpret_cast<const float4*>(rp + (size_t)gs.res * P.Cout));
-                  const float4 r3 = __ldg(reinterpret_cast<const float4*>(rp + (size_t)(gs.res + 1) * P.Cout));
-                  v.x += 0.25f * (r0.x + r1.x + r2.x + r3.x); v.y += 0.25f * (r0.y + r1.y + r2.y + r3.y);
-                  v.z += 0.25f * (r0.z + r1.z + r2.z + r3.z); v.w += 0.25f * (r0.w + r1.w + r2.w + r3.w);
-                }
-              }
-            }
-            if (P.qkv_heads) {
-              // q / k columns: 4 consecutive channels of one head, stored as split bf16 [B*H][L][D]
-              if (qk_kind < 2) {
-                const size_t o = (((size_t)b * P.qkv_heads + qk_hd) * g.L + tok) * qk_D + qk_d0;
-                tc_store_split(make_float4(v.x * qk_scale, v.y * qk_scale, v.z * qk_scale, v.w * qk_scale),
-                               qk_kind == 0 ? P.q_hi : P.k_hi, qk_kind == 0 ? P.q_lo : P.k_lo, o);
-              }
-            } else {
-              *reinterpret_cast<float4*>(P.out + m * P.Cout + n + cc) = v;
-            }
-            cs[0] += v.x; cs[1] += v.y; cs[2] += v.z; cs[3] += v.w;
-            cq[0] = fmaf(v.x, v.x, cq[0]); cq[1] = fmaf(v.y, v.y, cq[1]); cq[2] = fmaf(v.z, v.z, cq[2]); cq[3] = fmaf(v.w, v.w, cq[3]);
-          }
-        }
-        if (P.csum && P.ksplit <= 1 && (i & 1)) {
-          // rows 8*(i/2) .. +7 of this warp are complete: one (sample, plane) at every level -> flush their sums
+        for (int j = 0; j < 32; ++j) fv[j] = __uint_as_float(r[j]);
+        __syncwarp();
+        if (!T.small || T.spt == 1) tc_csum_chunk32(fv, live, lane, P.csum + (((size_t)(live ? b : 0) * 3 + pl_stat) * P.Cout + n) * 2);
+        else                        tc_csum_chunk(fv, live, lane, P.csum + (((size_t)(live ? b : 0) * 3 + pl_stat) * P.Cout + n) * 2);
+      }
+      if (have_next) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            cs[k] += __shfl_xor_sync(0xffffffffu, cs[k], 8);  cq[k] += __shfl_xor_sync(0xffffffffu, cq[k], 8);
-            cs[k] += __shfl_xor_sync(0xffffffffu, cs[k], 16); cq[k] += __shfl_xor_sync(0xffffffffu, cq[k], 16);
-          }
-          int b8, tok8; tc_row_map(T, q * 32 + 8 * (i >> 1), b8, tok8);
-          if (lane < 8 && b8 < P.B) {
-            const int p8 = tok8 < T.nxy ? 0 : (tok8 - T.nxy < T.npl ? 1 : 2);
-            double* dst = P.csum + (((size_t)b8 * 3 + p8) * P.Cout + n + cc) * 2;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) { atomicAdd(dst + 2 * k, (double)cs[k]); atomicAdd(dst + 2 * k + 1, (double)cq[k]); }
-          }
-#pragma unroll
-          for (int k = 0; k < 4; ++k) { cs[k] = 0.f; cq[k] = 0.f; }
-        }
+        for (int j = 0; j < 8; ++j) rpre[j] = rnext[j];
       }
     }
   }

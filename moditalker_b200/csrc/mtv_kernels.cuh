@@ -24,7 +24,7 @@
 
 namespace mtv {
 
-extern int g_mtv_use_pdl;   // 1 unless MTV_NO_PDL=1 (kernels_simt.cu)
+extern int g_mtv_use_pdl;   // 0 unless MTV_PDL=1 (kernels_simt.cu)
 
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {

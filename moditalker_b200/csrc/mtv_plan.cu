@@ -900,7 +900,9 @@ int mtv_create(const MtvConfig* cfg, MtvHandle* out) {
     const char* ng = getenv("MTV_NO_GRAPH");
     h->use_graph = !(ng && ng[0] == '1');
     if (const char* tm = getenv("MTV_TC_MASK")) h->tc_mask = (int)strtol(tm, nullptr, 0);
-    { const char* np = getenv("MTV_NO_PDL"); g_mtv_use_pdl = (np && np[0] == '1') ? 0 : 1; }
+    // programmatic dependent launch is opt-in: measured on B200 it costs ~5 % at B=1 (pre-launched CTAs
+    // contend with the running kernel) and gains nothing at B=8 — see profiles/README.md
+    { const char* np = getenv("MTV_PDL"); g_mtv_use_pdl = (np && np[0] == '1') ? 1 : 0; }
     register_weights(h.get());
     *out = h.release();
   });

@@ -15,4 +15,5 @@ cat gpurun_out/bench.json; tail -n 5 gpurun_out/bench.err
 timeout 300 python bench.py --chunks-per-gpu 8 --no-cpu-baseline > gpurun_out/bench_b8.json 2>> gpurun_out/bench.err
 cat gpurun_out/bench_b8.json
 timeout 120 python scripts/tc_timing.py 1 > gpurun_out/tc_timing_b1.log 2>&1; tail -30 gpurun_out/tc_timing_b1.log | head -5
-timeout 200 env MTV_NO_PDL=1 python bench.py --no-cpu-baseline > gpurun_out/bench_nopdl.json 2>> gpurun_out/bench.err; cat gpurun_out/bench_nopdl.json | cut -c1-400
+timeout 200 env MTV_PDL=1 python bench.py --no-cpu-baseline > gpurun_out/bench_pdl.json 2>> gpurun_out/bench.err; cat gpurun_out/bench_pdl.json | cut -c1-300
+timeout 200 env MTV_PDL=1 python bench.py --chunks-per-gpu 8 --no-cpu-baseline > gpurun_out/bench_b8_pdl.json 2>> gpurun_out/bench.err; cat gpurun_out/bench_b8_pdl.json | cut -c1-300
