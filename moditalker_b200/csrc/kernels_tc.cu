@@ -624,6 +624,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
       __syncwarp();
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
       const int n = n0 + c0;
+      // the chunk's bias is fetched in one go: loads inside the store loop would serialise behind the
+      // (possibly aliasing) stores and cost ~500 cycles each
+      float4 bpre[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) bpre[j] = P.bias ? __ldg(reinterpret_cast<const float4*>(P.bias + n) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
       float4 rnext[8];
       const bool have_next = pre_res && (c0 + 32 < BN);
       if (have_next) {
@@ -645,8 +650,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
           float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
-          if (P.bias) {
-            const float4 bv = __ldg(reinterpret_cast<const float4*>(P.bias + n + j));
+          {
+            const float4 bv = bpre[j >> 2];
             v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
           }
           if (P.resid) {
