@@ -9,8 +9,10 @@
 //                 [B*H][D][L], so every MMA operand is K-major and TMA-loadable.
 //   k_attn_tc<D>: one CTA = 128 queries of one (sample, head, segment).  Per 64-key block:
 //                 S = Q K^T            tcgen05.mma, 128x64 fp32 in TMEM (3 split-bf16 MMAs / k-step)
-//                 online softmax       4 warps, thread == query row: tcgen05.ld S, exp2, P -> smem
-//                                      as split bf16 in the UMMA 128B-swizzled K-major layout
+//                 online softmax       8 warps, two threads per query row (32 of the 64 key columns and half
+//                                      of the D output columns each; row max exchanged through smem):
+//                                      tcgen05.ld S, exp2, P -> smem as split bf16 in the UMMA
+//                                      128B-swizzled K-major layout
 //                 O_blk = P V          tcgen05.mma, 128xD fp32 in TMEM, folded into registers
 //                 The L x L score matrix never exists (reference: 134 MB per top-level call).
 //                 S(j+1) is issued while the softmax of block j runs.
@@ -94,6 +96,12 @@ __device__ __forceinline__ void a_tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
 }
+__device__ __forceinline__ void a_tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+      : "r"(taddr));
+}
 __device__ __forceinline__ void a_tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
@@ -149,7 +157,7 @@ cudaError_t launch_qkv_split(const QkvSplitParams& P, cudaStream_t s) {
 }
 
 // ------------------------------------------------------------------ attention
-constexpr int AT_BQ = 128, AT_BKV = 64, AT_THREADS = 192, AT_NS = 3;
+constexpr int AT_BQ = 128, AT_BKV = 64, AT_THREADS = 320, AT_NS = 3;   // warps: 0 TMA, 1 MMA, 2-5 / 6-9 softmax halves
 
 template <int D>
 struct AttnSmem {
@@ -174,6 +182,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) k_attn_tc(const __grid_constant
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_q, bar_full[AT_NS], bar_empty[AT_NS], bar_s_full, bar_s_free, bar_p_full, bar_o_full;
   __shared__ uint32_t tmem_base_s;
+  __shared__ float s_xchg[2][AT_BQ];      // per-row exchange between the two softmax halves (row max, final row sum)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem0 = (a_smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -197,7 +206,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) k_attn_tc(const __grid_constant
     a_mbar_init(&bar_q, 1);
     for (int s = 0; s < AT_NS; ++s) { a_mbar_init(&bar_full[s], 1); a_mbar_init(&bar_empty[s], 1); }
     a_mbar_init(&bar_s_full, 1); a_mbar_init(&bar_o_full, 1);
-    a_mbar_init(&bar_s_free, 128); a_mbar_init(&bar_p_full, 128);
+    a_mbar_init(&bar_s_free, 256); a_mbar_init(&bar_p_full, 256);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -284,65 +293,70 @@ __global__ void __launch_bounds__(AT_THREADS, 1) k_attn_tc(const __grid_constant
     MTV_PDL_TRIGGER();
   } else {
     // =============================== softmax / epilogue ==========================
-    const int qq = warp & 3;
+    // warps 2-5: key columns [0,32) of each S block and output columns [0, D/2);
+    // warps 6-9: key columns [32,64) and output columns [D/2, D).  Thread == (row, half).
+    constexpr int DH = D / 2;
+    const int half = (warp - 2) >> 2;             // 0 or 1
+    const int qq = warp & 3;                      // TMEM lane quarter this warp may read
     const int row = qq * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(qq * 32) << 16;
-    float m_run = -INFINITY, l_run = 0.f;
-    float o[D];
+    float m_run = -INFINITY, l_part = 0.f;
+    float o[DH];
 #pragma unroll
-    for (int d = 0; d < D; ++d) o[d] = 0.f;
+    for (int d = 0; d < DH; ++d) o[d] = 0.f;
 
-    auto fold_O = [&]() {   // o += O_blk (TMEM cols [64, 64+D))
+    auto fold_O = [&]() {   // o += this half's columns of O_blk (TMEM cols [64 + half*DH, +DH))
 #pragma unroll
-      for (int c = 0; c < D; c += 16) {
-        uint32_t r[16];
-        a_tmem_ld16(tmem_O + lane_addr + (uint32_t)c, r);
+      for (int c = 0; c < DH; c += 8) {
+        uint32_t r[8];
+        a_tmem_ld8(tmem_O + lane_addr + (uint32_t)(half * DH + c), r);
         a_tmem_wait_ld();
 #pragma unroll
-        for (int i = 0; i < 16; ++i) o[c + i] += __uint_as_float(r[i]);
+        for (int i = 0; i < 8; ++i) o[c + i] += __uint_as_float(r[i]);
       }
     };
 
     for (int j = 0; j < nblk; ++j) {
       a_mbar_wait(&bar_s_full, (uint32_t)(j & 1));
       a_fence_after();
-      float s[AT_BKV];
+      float s[32];
       {
         uint32_t r[32];
-        a_tmem_ld32(tmem_S + lane_addr, r);
+        a_tmem_ld32(tmem_S + lane_addr + (uint32_t)(half * 32), r);
         a_tmem_wait_ld();
 #pragma unroll
         for (int i = 0; i < 32; ++i) s[i] = __uint_as_float(r[i]);
-        a_tmem_ld32(tmem_S + lane_addr + 32u, r);
-        a_tmem_wait_ld();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) s[32 + i] = __uint_as_float(r[i]);
       }
       a_fence_before();
       a_mbar_arrive(&bar_s_free);                           // S TMEM may be overwritten by S(j+1)
-      const int valid = min(AT_BKV, len - j * AT_BKV);
+      const int valid = min(32, len - j * AT_BKV - half * 32);   // may be <= 0 for the upper half of a short tail
       float mx = -INFINITY;
 #pragma unroll
-      for (int i = 0; i < AT_BKV; ++i) { if (i >= valid) s[i] = -INFINITY; mx = fmaxf(mx, s[i]); }
-      const float m_new = fmaxf(m_run, mx);
+      for (int i = 0; i < 32; ++i) { if (i >= valid) s[i] = -INFINITY; mx = fmaxf(mx, s[i]); }
+      // row max over both halves
+      s_xchg[half][row] = mx;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      mx = fmaxf(mx, s_xchg[half ^ 1][row]);
+      const float m_new = fmaxf(m_run, mx);                 // finite: the lower half always holds a valid key
       const float corr = exp2f(m_run - m_new);
       float sum = 0.f;
 #pragma unroll
-      for (int i = 0; i < AT_BKV; ++i) { s[i] = exp2f(s[i] - m_new); sum += s[i]; }
+      for (int i = 0; i < 32; ++i) { s[i] = exp2f(s[i] - m_new); sum += s[i]; }
       if (j > 0) {                                          // O block (j-1) finished -> fold it in before rescaling
         a_mbar_wait(&bar_o_full, (uint32_t)((j - 1) & 1));
         a_fence_after();
         fold_O();
       }
-      l_run = l_run * corr + sum;
+      l_part = l_part * corr + sum;
       m_run = m_new;
 #pragma unroll
-      for (int d = 0; d < D; ++d) o[d] *= corr;
-      // P(j) -> smem, split bf16, 128B-swizzled K-major rows (16-byte chunk c of row r at c ^ (r & 7))
+      for (int d = 0; d < DH; ++d) o[d] *= corr;
+      // P(j) -> smem, split bf16, 128B-swizzled K-major rows (16-byte chunk c of row r at c ^ (r & 7));
+      // this half owns chunks [4*half, 4*half + 4)
       {
         const uint32_t rbase_hi = sP_hi + (uint32_t)row * 128u, rbase_lo = sP_lo + (uint32_t)row * 128u;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
+        for (int c = 0; c < 4; ++c) {
           uint32_t hi[4], lo[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
@@ -351,7 +365,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) k_attn_tc(const __grid_constant
             hi[e] = pack_bf16(__bfloat162float(h0), __bfloat162float(h1));
             lo[e] = pack_bf16(p0 - __bfloat162float(h0), p1 - __bfloat162float(h1));
           }
-          const uint32_t off = (uint32_t)((c ^ (row & 7)) * 16);
+          const uint32_t off = (uint32_t)((((half << 2) | c) ^ (row & 7)) * 16);
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rbase_hi + off), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rbase_lo + off), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
         }
@@ -359,21 +373,29 @@ __global__ void __launch_bounds__(AT_THREADS, 1) k_attn_tc(const __grid_constant
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA (async proxy)
       a_fence_before();
       a_mbar_arrive(&bar_p_full);
+      // the exchange slots are rewritten next block: everyone has read them once this barrier-protected
+      // point is passed by both halves (the next write happens after the next bar_s_full wait + tcgen05.ld,
+      // and the partner's read above precedes its arrive on bar_p_full, which precedes S(j+1)... keep it simple:
+      asm volatile("bar.sync 1, 256;" ::: "memory");
     }
     a_mbar_wait(&bar_o_full, (uint32_t)((nblk - 1) & 1));
     MTV_PDL_TRIGGER();
     a_fence_after();
     fold_O();
+    // total row sum = both halves' partial sums
+    s_xchg[half][row] = l_part;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    const float l_run = l_part + s_xchg[half ^ 1][row];
     const int q = q0 + row;
     if (q < len) {
       const int b = bh / P.heads, h = bh - b * P.heads;
       const float inv = 1.0f / l_run;
-      const size_t oidx = ((size_t)b * P.L + t_lo + q) * P.C + h * D;
+      const size_t oidx = ((size_t)b * P.L + t_lo + q) * P.C + h * D + half * DH;
       if (P.out_hi) {       // split-bf16 A operand of the proj_out GEMM, written in place of the fp32 tensor
         __nv_bfloat16* oh = reinterpret_cast<__nv_bfloat16*>(P.out_hi) + oidx;
         __nv_bfloat16* ol = reinterpret_cast<__nv_bfloat16*>(P.out_lo) + oidx;
 #pragma unroll
-        for (int d = 0; d < D; d += 8) {
+        for (int d = 0; d < DH; d += 8) {
           __align__(16) __nv_bfloat16 hh[8], ll[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -386,7 +408,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) k_attn_tc(const __grid_constant
       } else {
         float* dst = P.out + oidx;
 #pragma unroll
-        for (int d = 0; d < D; d += 4)
+        for (int d = 0; d < DH; d += 4)
           *reinterpret_cast<float4*>(dst + d) = make_float4(o[d] * inv, o[d + 1] * inv, o[d + 2] * inv, o[d + 3] * inv);
       }
     }

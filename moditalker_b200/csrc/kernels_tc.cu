@@ -119,22 +119,27 @@ __global__ void __launch_bounds__(256) k_apply_norm_split(const __grid_constant_
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const Geo gs = P.resample == RS_NONE ? g : (P.resample == RS_UP2 ? geo_down(g) : geo_up(g));
   const double cnt = (double)cpg * (P.joint ? (double)gs.L : (double)(p == 0 ? gs.res * gs.res : gs.t * gs.res));
-  for (int grp = warp; grp < 32; grp += 8) {
+  {
+    // 32 groups in one pass: warp w owns groups 4w..4w+3, 8 lanes per group (one load latency, not four)
+    const int grp = warp * 4 + (lane >> 3);
     double s = 0.0, ss = 0.0;
-    for (int ci = lane; ci < cpg; ci += 32) {
+    for (int ci = lane & 7; ci < cpg; ci += 8) {
       const int c = grp * cpg + ci;
       const double* cs; int Cs, cc;
       if (c < P.C0) { cs = P.csum0; Cs = P.C0; cc = c; } else { cs = P.csum1; Cs = P.C1; cc = c - P.C0; }
       if (P.joint) {
-#pragma unroll
-        for (int pp = 0; pp < 3; ++pp) { const double* q = cs + (((size_t)b * 3 + pp) * Cs + cc) * 2; s += q[0]; ss += q[1]; }
+        const double2 q0 = *reinterpret_cast<const double2*>(cs + (((size_t)b * 3 + 0) * Cs + cc) * 2);
+        const double2 q1 = *reinterpret_cast<const double2*>(cs + (((size_t)b * 3 + 1) * Cs + cc) * 2);
+        const double2 q2 = *reinterpret_cast<const double2*>(cs + (((size_t)b * 3 + 2) * Cs + cc) * 2);
+        s += q0.x + q1.x + q2.x; ss += q0.y + q1.y + q2.y;
       } else {
-        const double* q = cs + (((size_t)b * 3 + p) * Cs + cc) * 2; s += q[0]; ss += q[1];
+        const double2 q0 = *reinterpret_cast<const double2*>(cs + (((size_t)b * 3 + p) * Cs + cc) * 2);
+        s += q0.x; ss += q0.y;
       }
     }
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, off); ss += __shfl_xor_sync(0xffffffffu, ss, off); }
-    if (lane == 0) {
+    for (int off = 4; off > 0; off >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, off); ss += __shfl_xor_sync(0xffffffffu, ss, off); }
+    if ((lane & 7) == 0) {
       const double mean = s / cnt;
       double var = ss / cnt - mean * mean; var = var < 0.0 ? 0.0 : var;
       s_mean[grp] = mean; s_rstd[grp] = rsqrt(var + 1e-5);
@@ -763,8 +768,18 @@ __global__ void __launch_bounds__(256) k_tc_splitk_epilogue(const __grid_constan
   const size_t m = (size_t)blockIdx.x * 32 + lane;
   const int n = blockIdx.y * 32 + wq * 4;
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int z = 0; z < P.ksplit; ++z) {
-    const float4 v = *reinterpret_cast<const float4*>(P.partial + ((size_t)z * M + m) * P.Cout + n);
+  const float* pp = P.partial + m * P.Cout + n;
+  const size_t zstride = M * P.Cout;
+  int z = 0;
+  for (; z + 8 <= P.ksplit; z += 8) {           // 8 independent loads in flight, fixed summation order
+    float4 v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __ldcs(reinterpret_cast<const float4*>(pp + (size_t)(z + i) * zstride));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s.x += v[i].x; s.y += v[i].y; s.z += v[i].z; s.w += v[i].w; }
+  }
+  for (; z < P.ksplit; ++z) {
+    const float4 v = __ldcs(reinterpret_cast<const float4*>(pp + (size_t)z * zstride));
     s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
   }
   if (P.bias) { const float4 bv = __ldg(reinterpret_cast<const float4*>(P.bias + n)); s.x += bv.x; s.y += bv.y; s.z += bv.z; s.w += bv.w; }

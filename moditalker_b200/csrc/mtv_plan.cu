@@ -498,8 +498,9 @@ struct Builder {
     const int iters = T.taps * (T.Cin / 64) + T.Cin2 / 64;
     const int base = mtiles * (P.Cout / bn);
     int ks = 1;
-    if (base < 64 && iters >= 32 && ((h->tc_mask >> 5) & 1) && !o.qkv) {
-      ks = std::min(iters / 4, (h->num_sms + base - 1) / base);
+    if (iters >= 32 && ((h->tc_mask >> 5) & 1) && !o.qkv && base * 2 <= h->num_sms + h->num_sms / 4) {
+      // spread a fixed amount of shared-memory / weight traffic over (nearly) all SMs
+      ks = std::min(iters / 4, std::max(1, h->num_sms / base));
       ks = std::min(ks, 32);
       while (ks > 1 && (ks - 1) * ((iters + ks - 1) / ks) >= iters) --ks;
     }
@@ -1051,16 +1052,40 @@ int mtv_profile_forward(MtvHandle h, const float* x, const float* cond, const fl
     // the per-launch average then carries the steady-state launch gap, not the event overhead
     int reps = 1;
     if (const char* rp = getenv("MTV_PROFILE_REPS")) reps = std::max(1, atoi(rp));
+    // Graph-body ops are timed as a private CUDA graph holding `reps` copies of the launch, so the
+    // host's per-launch cost (several microseconds, more than many of these kernels run) stays out of
+    // the measurement; ops that read caller pointers are timed eagerly.
+    const char* pg = getenv("MTV_PROFILE_EAGER");
+    const bool use_graph = !(pg && pg[0] == '1');
     int k = 0;
     for (Op& op : pl->ops) {
-      CK(cudaEventRecord(e0, s));
-      for (int r = 0; r < reps; ++r) {
-        cudaError_t e = op.fn(s);
-        if (e != cudaSuccess) throw MtvError("launch failed at " + op.name + ": " + cudaGetErrorString(e));
+      float ms = 0;
+      if (use_graph && op.phase == 1) {
+        cudaStream_t cs = h->capture_stream();
+        cudaGraph_t g = nullptr; cudaGraphExec_t ge = nullptr;
+        CK(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+        cudaError_t e = cudaSuccess;
+        for (int r = 0; r < reps && e == cudaSuccess; ++r) e = op.fn(cs);
+        cudaError_t e2 = cudaStreamEndCapture(cs, &g);
+        if (e != cudaSuccess || e2 != cudaSuccess) { if (g) cudaGraphDestroy(g); throw MtvError("capture failed at " + op.name); }
+        CK(cudaGraphInstantiate(&ge, g, 0));
+        CK(cudaGraphLaunch(ge, s));               // warm
+        CK(cudaEventRecord(e0, s));
+        CK(cudaGraphLaunch(ge, s));
+        CK(cudaEventRecord(e1, s));
+        CK(cudaEventSynchronize(e1));
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        cudaGraphExecDestroy(ge); cudaGraphDestroy(g);
+      } else {
+        CK(cudaEventRecord(e0, s));
+        for (int r = 0; r < reps; ++r) {
+          cudaError_t e = op.fn(s);
+          if (e != cudaSuccess) throw MtvError("launch failed at " + op.name + ": " + cudaGetErrorString(e));
+        }
+        CK(cudaEventRecord(e1, s));
+        CK(cudaEventSynchronize(e1));
+        CK(cudaEventElapsedTime(&ms, e0, e1));
       }
-      CK(cudaEventRecord(e1, s));
-      CK(cudaEventSynchronize(e1));
-      float ms = 0; CK(cudaEventElapsedTime(&ms, e0, e1));
       ms /= (float)reps;
       if (k < cap) {
         MtvKernelTime& kt = entries[k];
