@@ -174,7 +174,7 @@ struct AttnSmem {
 };
 
 template <int D>
-__global__ void __launch_bounds__(AT_THREADS, 1) k_attn_tc(const __grid_constant__ AttnTcParams P) {
+__global__ void __launch_bounds__(AT_THREADS, (D <= 32) ? 2 : 1) k_attn_tc(const __grid_constant__ AttnTcParams P) {
   using SM = AttnSmem<D>;
   constexpr uint32_t IDESC_S = a_idesc(AT_BQ, AT_BKV);
   constexpr uint32_t IDESC_O = a_idesc(AT_BQ, D);

@@ -336,6 +336,17 @@ cudaError_t tc_debug_arm(long long* buf, unsigned int cap) {
 cudaError_t tc_debug_count(unsigned int* n) { return cudaMemcpyFromSymbol(n, g_tc_dbg_count, sizeof(*n)); }
 __device__ __forceinline__ long long gtime_ns() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 
+// 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256): a lane that owns a 128-byte row segment moves it in
+// four full 32-byte sectors instead of eight half sectors — the row-per-lane epilogue is LSU-transaction bound
+__device__ __forceinline__ void st_global_v8(float* p, const float* v) {
+  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
+               "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+}
+__device__ __forceinline__ void ld_global_nc_v8(const float* p, float* v) {
+  asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "l"(p));
+}
+
 // ------------------------------------------------------------------ the tap-GEMM
 constexpr int TC_BM = 128, TC_BK = 64, TC_THREADS = 192;
 __host__ __device__ constexpr int tc_stage_bytes(int BN) { return 2 * TC_BM * 128 + 2 * BN * 128; }
@@ -610,11 +621,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
     MTV_PDL_WAIT();                                 // residual / statistics buffers belong to earlier kernels
     // the residual and bias of the first 32-column chunk are fetched while the MMAs still run
     const bool pre_res = live && P.resid && P.resid_mode == RS_NONE && P.ksplit <= 1;
-    float4 rpre[8];
+    float rpre[32];
     if (pre_res) {
-      const float4* rp4 = reinterpret_cast<const float4*>(P.resid + m * P.Cout + n0);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) rpre[j] = __ldg(rp4 + j);
+      for (int j = 0; j < 4; ++j) ld_global_nc_v8(P.resid + m * P.Cout + n0 + 8 * j, rpre + 8 * j);
     }
     mbar_wait(&bar_acc, 0);
     MTV_PDL_TRIGGER();
@@ -634,21 +644,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
       float4 bpre[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) bpre[j] = P.bias ? __ldg(reinterpret_cast<const float4*>(P.bias + n) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-      float4 rnext[8];
+      float rnext[32];
       const bool have_next = pre_res && (c0 + 32 < BN);
       if (have_next) {
-        const float4* rp4 = reinterpret_cast<const float4*>(P.resid + m * P.Cout + n + 32);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) rnext[j] = __ldg(rp4 + j);
+        for (int j = 0; j < 4; ++j) ld_global_nc_v8(P.resid + m * P.Cout + n + 32 + 8 * j, rnext + 8 * j);
       }
       if (!live) {
         // rows of samples beyond the batch (partial last tile of a small level): nothing to store
       } else if (P.ksplit > 1) {
         float* dst = P.partial + ((size_t)blockIdx.z * ((size_t)P.B * g.L) + m) * P.Cout + n;
+        float pv[32];
 #pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
-                                                            __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+        for (int j = 0; j < 32; ++j) pv[j] = __uint_as_float(r[j]);
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) st_global_v8(dst + j, pv + j);
       } else {
         float* dst = P.out + m * P.Cout + n;
         float fv[32];
@@ -661,8 +671,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
           }
           if (P.resid) {
             if (P.resid_mode == RS_NONE) {
-              const float4 rv = rpre[j >> 2];
-              v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
+              v.x += rpre[j]; v.y += rpre[j + 1]; v.z += rpre[j + 2]; v.w += rpre[j + 3];
             } else if (P.resid_mode == RS_UP2) {
               const Geo gs = geo_down(g);
               const int ts = tc_plane_off(gs, p) + (y >> 1) * gs.res + (x >> 1);
@@ -680,8 +689,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
               v.z += 0.25f * (r0.z + r1.z + r2.z + r3.z); v.w += 0.25f * (r0.w + r1.w + r2.w + r3.w);
             }
           }
-          if (!P.qkv_heads) *reinterpret_cast<float4*>(dst + j) = v;
           fv[j] = v.x; fv[j + 1] = v.y; fv[j + 2] = v.z; fv[j + 3] = v.w;
+        }
+        if (!P.qkv_heads) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) st_global_v8(dst + j, fv + j);
         }
         if (P.qkv_heads) {
           // channels are head-major [h: q(D) k(D) v(D)] (unet.py:321); D >= 16, so every aligned run of 16
@@ -731,7 +743,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
       }
       if (have_next) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) rpre[j] = rnext[j];
+        for (int j = 0; j < 32; ++j) rpre[j] = rnext[j];
       }
     }
   }
