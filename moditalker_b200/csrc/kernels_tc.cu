@@ -119,6 +119,18 @@ __global__ void __launch_bounds__(256) k_apply_norm_split(const __grid_constant_
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const Geo gs = P.resample == RS_NONE ? g : (P.resample == RS_UP2 ? geo_down(g) : geo_up(g));
   const double cnt = (double)cpg * (P.joint ? (double)gs.L : (double)(p == 0 ? gs.res * gs.res : gs.t * gs.res));
+  // gamma / beta / FiLM rows are read once per step and have left L2 by then: issue their (DRAM-latency)
+  // loads first so they overlap the statistics pass instead of following it
+  float pg[8], pb[8], psc[8], psh[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int c = tid + 256 * k;
+    pg[k] = pb[k] = psc[k] = psh[k] = 0.f;
+    if (c < C) {
+      pg[k] = __ldg(P.gamma + c); pb[k] = __ldg(P.beta + c);
+      if (P.film) { const float* f = P.film + (size_t)b * P.film_stride; psc[k] = __ldg(f + c); psh[k] = __ldg(f + C + c); }
+    }
+  }
   {
     // 32 groups in one pass: warp w owns groups 4w..4w+3, 8 lanes per group (one load latency, not four)
     const int grp = warp * 4 + (lane >> 3);
@@ -147,16 +159,16 @@ __global__ void __launch_bounds__(256) k_apply_norm_split(const __grid_constant_
   }
   __syncthreads();
   float* sa = s_aff; float* sd = s_aff + C;
-  for (int c = tid; c < C; c += 256) {
-    const int grp = c / cpg;
-    double a = s_rstd[grp] * (double)__ldg(P.gamma + c);
-    double d = (double)__ldg(P.beta + c) - s_mean[grp] * a;
-    if (P.film) {
-      const float* f = P.film + (size_t)b * P.film_stride;
-      const double sc = 1.0 + (double)__ldg(f + c);
-      a *= sc; d = d * sc + (double)__ldg(f + C + c);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int c = tid + 256 * k;
+    if (c < C) {
+      const int grp = c / cpg;
+      double a = s_rstd[grp] * (double)pg[k];
+      double d = (double)pb[k] - s_mean[grp] * a;
+      if (P.film) { const double sc = 1.0 + (double)psc[k]; a *= sc; d = d * sc + (double)psh[k]; }
+      sa[c] = (float)a; sd[c] = (float)d;
     }
-    sa[c] = (float)a; sd[c] = (float)d;
   }
   __syncthreads();
   const int cq = C >> 2;
@@ -496,6 +508,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
   __shared__ __align__(8) uint64_t bar_full[NS], bar_empty[NS], bar_acc;
   __shared__ uint32_t tmem_base_s;
   __shared__ long long s_stamp[8];
+  __shared__ __align__(16) float s_bias[128];      // this CTA's BN bias values, fetched while the main loop runs
   const bool dbg = g_tc_dbg != nullptr;
   long long g_t0 = 0;
   if (dbg && threadIdx.x == 0) { s_stamp[0] = clock64(); g_t0 = gtime_ns(); }
@@ -619,7 +632,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
     const bool live = b < P.B;
     const size_t m = (size_t)b * g.L + tok;
     MTV_PDL_WAIT();                                 // residual / statistics buffers belong to earlier kernels
-    // the residual and bias of the first 32-column chunk are fetched while the MMAs still run
+    // Bias: small, touched once per step and evicted from L2 by the weight stream in between, i.e. a DRAM
+    // miss (~2000 cycles) if loaded on demand per chunk — so it is staged in smem during the main loop.
+    {
+      const int te = threadIdx.x - 64;
+      if (te < BN) s_bias[te] = P.bias ? __ldg(P.bias + n0 + te) : 0.0f;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
+    // the residual of the first 32-column chunk is fetched while the MMAs still run
     const bool pre_res = live && P.resid && P.resid_mode == RS_NONE && P.ksplit <= 1;
     float rpre[32];
     if (pre_res) {
@@ -643,7 +663,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
       // (possibly aliasing) stores and cost ~500 cycles each
       float4 bpre[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) bpre[j] = P.bias ? __ldg(reinterpret_cast<const float4*>(P.bias + n) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int j = 0; j < 8; ++j) bpre[j] = *reinterpret_cast<const float4*>(&s_bias[c0 + 4 * j]);
       float rnext[32];
       const bool have_next = pre_res && (c0 + 32 < BN);
       if (have_next) {
@@ -779,6 +799,8 @@ __global__ void __launch_bounds__(256) k_tc_splitk_epilogue(const __grid_constan
   const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
   const size_t m = (size_t)blockIdx.x * 32 + lane;
   const int n = blockIdx.y * 32 + wq * 4;
+  float4 bv0 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (P.bias) bv0 = __ldg(reinterpret_cast<const float4*>(P.bias + n));     // cold line: issue first
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
   const float* pp = P.partial + m * P.Cout + n;
   const size_t zstride = M * P.Cout;
@@ -794,7 +816,7 @@ __global__ void __launch_bounds__(256) k_tc_splitk_epilogue(const __grid_constan
     const float4 v = __ldcs(reinterpret_cast<const float4*>(pp + (size_t)z * zstride));
     s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
   }
-  if (P.bias) { const float4 bv = __ldg(reinterpret_cast<const float4*>(P.bias + n)); s.x += bv.x; s.y += bv.y; s.z += bv.z; s.w += bv.w; }
+  s.x += bv0.x; s.y += bv0.y; s.z += bv0.z; s.w += bv0.w;
   const int b = (int)(m / g.L), tok = (int)(m - (size_t)b * g.L);
   int p = 0, y = 0, x = 0;
   tc_decode_tok(g, tok, p, y, x);
