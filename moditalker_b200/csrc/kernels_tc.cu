@@ -499,7 +499,11 @@ __device__ __forceinline__ void tc_csum_chunk32(float (&v)[32], bool live, int l
   }
 }
 
-template <int BN>
+// EPI selects the epilogue at compile time (the row-per-lane epilogue is instruction-issue bound, so the
+// paths a launch cannot take must not even be predicated off):
+//   0 split-K partial tile, 1 bias [+ same-geometry residual] [+ GroupNorm sums], 2 qkv operand split,
+//   3 residual through nearest-up / avg-pool geometry (up / down ResBlocks with identity skip)
+template <int BN, int EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant__ TcConvParams P) {
   constexpr int NS = tc_stages(BN);
   constexpr int STAGE = tc_stage_bytes(BN);
@@ -640,7 +644,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
       asm volatile("bar.sync 1, 128;" ::: "memory");
     }
     // the residual of the first 32-column chunk is fetched while the MMAs still run
-    const bool pre_res = live && P.resid && P.resid_mode == RS_NONE && P.ksplit <= 1;
+    const bool pre_res = EPI == 1 && live && P.resid;
     float rpre[32];
     if (pre_res) {
 #pragma unroll
@@ -651,7 +655,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
     if (dbg && threadIdx.x == 64) s_stamp[5] = clock64();            // accumulator complete
     tc_fence_after();
     int p = 0, y = 0, x = 0;
-    if ((P.resid && P.resid_mode != RS_NONE) || P.csum) tc_decode_fast(T, tok, p, y, x);
+    if (EPI == 3 || ((EPI == 1) && P.csum)) tc_decode_fast(T, tok, p, y, x);
     const int pl_stat = p;
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
@@ -672,7 +676,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
       }
       if (!live) {
         // rows of samples beyond the batch (partial last tile of a small level): nothing to store
-      } else if (P.ksplit > 1) {
+      } else if constexpr (EPI == 0) {
         float* dst = P.partial + ((size_t)blockIdx.z * ((size_t)P.B * g.L) + m) * P.Cout + n;
         float pv[32];
 #pragma unroll
@@ -689,10 +693,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
             const float4 bv = bpre[j >> 2];
             v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
           }
-          if (P.resid) {
-            if (P.resid_mode == RS_NONE) {
-              v.x += rpre[j]; v.y += rpre[j + 1]; v.z += rpre[j + 2]; v.w += rpre[j + 3];
-            } else if (P.resid_mode == RS_UP2) {
+          if constexpr (EPI == 1) {
+            if (P.resid) { v.x += rpre[j]; v.y += rpre[j + 1]; v.z += rpre[j + 2]; v.w += rpre[j + 3]; }
+          }
+          if constexpr (EPI == 3) {
+            if (P.resid_mode == RS_UP2) {
               const Geo gs = geo_down(g);
               const int ts = tc_plane_off(gs, p) + (y >> 1) * gs.res + (x >> 1);
               const float4 rv = __ldg(reinterpret_cast<const float4*>(P.resid + ((size_t)b * gs.L + ts) * P.Cout + n + j));
@@ -711,11 +716,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
           }
           fv[j] = v.x; fv[j + 1] = v.y; fv[j + 2] = v.z; fv[j + 3] = v.w;
         }
-        if (!P.qkv_heads) {
+        if constexpr (EPI != 2) {
 #pragma unroll
           for (int j = 0; j < 32; j += 8) st_global_v8(dst + j, fv + j);
         }
-        if (P.qkv_heads) {
+        if constexpr (EPI == 2) {
           // channels are head-major [h: q(D) k(D) v(D)] (unet.py:321); D >= 16, so every aligned run of 16
           // channels is one of q / k / v of one head
           const int Dh = P.Cout / (3 * P.qkv_heads);
@@ -748,12 +753,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
             }
           }
         }
-        if (P.csum) {   // uniform branch: statistics of the tensor just written, for the next GroupNorm
+        if ((EPI == 1 || EPI == 3) && P.csum) {   // uniform: statistics of the tensor just written, for the next GroupNorm
 #pragma unroll
           for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(fv[j]);
         }
       }
-      if (P.csum && P.ksplit <= 1) {
+      if ((EPI == 1 || EPI == 3) && P.csum) {
         float fv[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) fv[j] = __uint_as_float(r[j]);
@@ -863,16 +868,23 @@ cudaError_t launch_conv_tc(const TcConvParams& P, cudaStream_t s) {
   const int M = P.B * P.geo.L;
   const int tiles = P.geo.L > TC_BM ? M / TC_BM : (P.B + (TC_BM / P.geo.L) - 1) / (TC_BM / P.geo.L);
   dim3 grid(tiles, P.Cout / BN, P.ksplit > 1 ? P.ksplit : 1);
-  cudaError_t e;
+  cudaError_t e = cudaSuccess;
+  const int epi = P.ksplit > 1 ? 0 : (P.qkv_heads ? 2 : ((P.resid && P.resid_mode != RS_NONE) ? 3 : 1));
+#define MTV_TC_LAUNCH(BN_, EPI_)                                                                                   \
+  do {                                                                                                             \
+    e = cudaFuncSetAttribute(k_conv_tc<BN_, EPI_>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(BN_)); \
+    if (e != cudaSuccess) return e;                                                                                \
+    e = launch_k(k_conv_tc<BN_, EPI_>, grid, dim3(TC_THREADS), (size_t)tc_smem_bytes(BN_), s, P);                   \
+    if (e != cudaSuccess) return e;                                                                                \
+  } while (0)
   if (BN == 64) {
-    e = cudaFuncSetAttribute(k_conv_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(64));
-    if (e != cudaSuccess) return e;
-    { cudaError_t le_ = launch_k(k_conv_tc<64>, dim3(grid), dim3(TC_THREADS), (size_t)(tc_smem_bytes(64)), s, P); if (le_ != cudaSuccess) return le_; }
+    switch (epi) { case 0: MTV_TC_LAUNCH(64, 0); break; case 1: MTV_TC_LAUNCH(64, 1); break;
+                   case 2: MTV_TC_LAUNCH(64, 2); break; default: MTV_TC_LAUNCH(64, 3); break; }
   } else {
-    e = cudaFuncSetAttribute(k_conv_tc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(128));
-    if (e != cudaSuccess) return e;
-    { cudaError_t le_ = launch_k(k_conv_tc<128>, dim3(grid), dim3(TC_THREADS), (size_t)(tc_smem_bytes(128)), s, P); if (le_ != cudaSuccess) return le_; }
+    switch (epi) { case 0: MTV_TC_LAUNCH(128, 0); break; case 1: MTV_TC_LAUNCH(128, 1); break;
+                   case 2: MTV_TC_LAUNCH(128, 2); break; default: MTV_TC_LAUNCH(128, 3); break; }
   }
+#undef MTV_TC_LAUNCH
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   if (P.ksplit > 1) {
