@@ -176,6 +176,7 @@ struct AttnSmem {
 template <int D>
 __global__ void __launch_bounds__(AT_THREADS, (D <= 32) ? 2 : 1) k_attn_tc(const __grid_constant__ AttnTcParams P) {
   using SM = AttnSmem<D>;
+  mtv_prefetch_slice(P.pf0, P.pf1, P.pf_bytes, blockIdx.x + gridDim.x * blockIdx.y, gridDim.x * gridDim.y);
   constexpr uint32_t IDESC_S = a_idesc(AT_BQ, AT_BKV);
   constexpr uint32_t IDESC_O = a_idesc(AT_BQ, D);
   constexpr int TMEM_COLS = 128;                           // S: cols [0,64), O block: cols [64, 64+D)

@@ -265,10 +265,10 @@ static inline int conv_bm(const ConvParams& P, int num_sms) {
   return 32;
 }
 int conv_simt_pick_ksplit(const ConvParams& P, int num_sms) {
-  if (P.Cout <= 16) return 1;
   const int M = P.B * P.geo.L;
   const int bm = conv_bm(P, num_sms);
-  const int base = ((M + bm - 1) / bm) * ((P.Cout + 63) / 64);
+  const int bn = P.Cout <= 16 ? 16 : 64;
+  const int base = ((M + bm - 1) / bm) * ((P.Cout + bn - 1) / bn);
   if (base >= num_sms) return 1;
   const int iters = conv_iters(P);
   int ks = (4 * num_sms + base - 1) / base;

@@ -49,6 +49,7 @@ __device__ __forceinline__ void tc_store_split(const float4& v, void* hi_base, v
 
 __global__ void __launch_bounds__(256) k_apply_split(const __grid_constant__ ApplyParams P) {
   MTV_PDL_TRIGGER();
+  mtv_prefetch_slice(P.pf0, P.pf1, P.pf_bytes, blockIdx.x, gridDim.x);
   MTV_PDL_WAIT();
   const int C = P.C0 + P.C1;
   const int cq = C >> 2;
@@ -106,6 +107,8 @@ __global__ void __launch_bounds__(256) k_apply_split(const __grid_constant__ App
 // (FiLM folded in), then the body is k_apply_split's.
 __global__ void __launch_bounds__(256) k_apply_norm_split(const __grid_constant__ ApplyParams P) {
   MTV_PDL_TRIGGER();
+  mtv_prefetch_slice(P.pf0, P.pf1, P.pf_bytes, blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z),
+                     gridDim.x * gridDim.y * gridDim.z);
   MTV_PDL_WAIT();
   extern __shared__ float s_aff[];                 // a[C] | d[C]
   __shared__ double s_mean[32], s_rstd[32];

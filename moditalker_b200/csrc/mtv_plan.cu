@@ -160,7 +160,7 @@ struct MtvHandle_t {
   std::map<int, std::unique_ptr<Plan>> plans;
   Plan* last_plan = nullptr;
   int64_t weight_bytes = 0;
-  int tc_mask = 0x3ff;
+  int tc_mask = 0x7ff;
   cudaStream_t cap_stream = nullptr;
   cudaStream_t capture_stream() {
     if (!cap_stream) CK(cudaStreamCreateWithFlags(&cap_stream, cudaStreamNonBlocking));
@@ -398,7 +398,8 @@ struct Builder {
     return true;
   }
   // split-bf16 operand of one K-segment (+ optionally the un-normalised split of the same source)
-  SplitBuf emit_apply(const std::string& name, const KSeg& S, const Geo& g, int norm_id, SplitBuf* raw_out) {
+  SplitBuf emit_apply(const std::string& name, const KSeg& S, const Geo& g, int norm_id, SplitBuf* raw_out,
+                      const float* consumer_w = nullptr, int consumer_cout = 0) {
     const int C = S.C0 + S.C1;
     const size_t bytes = (size_t)B * g.L * C * 2;
     SplitBuf out; out.hi = dalloc(bytes); out.lo = dalloc(bytes);
@@ -406,6 +407,10 @@ struct Builder {
     A.src0 = S.src0; A.src1 = S.src1; A.C0 = S.C0; A.C1 = S.C1;
     A.silu = S.silu; A.resample = S.resample; A.B = B; A.geo = g; A.hi = out.hi; A.lo = out.lo;
     if (raw_out) { raw_out->hi = dalloc(bytes); raw_out->lo = dalloc(bytes); A.raw_hi = raw_out->hi; A.raw_lo = raw_out->lo; }
+    if (consumer_w && ((h->tc_mask >> 10) & 1)) {
+      auto it = h->tc_w.find(consumer_w);
+      if (it != h->tc_w.end()) { A.pf0 = it->second.first; A.pf1 = it->second.second; A.pf_bytes = (unsigned long long)S.taps * C * consumer_cout * 2; }
+    }
     if (norm_id >= 0) {
       const NormSpec& n = norms[norm_id];
       if (fuse_gn() && n.x0.csum && (!n.has_x1 || n.x1.csum)) {
@@ -474,7 +479,7 @@ struct Builder {
     if (P.Cout % 128 == 0 && mtiles * (P.Cout / 128) >= 64) bn = 128;   // fewer smem bytes per MMA once the SMs are covered
     T.bn = bn;
     {
-      const SplitBuf a0 = o.pre0 ? *o.pre0 : emit_apply(name, S, P.geo, norm0, o.raw_out);
+      const SplitBuf a0 = o.pre0 ? *o.pre0 : emit_apply(name, S, P.geo, norm0, o.raw_out, S.w, P.Cout);
       make_A_maps(a0, T.Cin, S.taps, P.geo, T.tmA_hi, T.tmA_lo);
     }
     auto wmaps = [&](const KSeg& K, CUtensorMap& whi, CUtensorMap& wlo) {
@@ -651,6 +656,10 @@ struct Builder {
         const size_t bytes = (size_t)B * L * C * 2;
         att_split.hi = dalloc(bytes); att_split.lo = dalloc(bytes);
         T.out_hi = att_split.hi; T.out_lo = att_split.lo;
+        if ((h->tc_mask >> 10) & 1) {
+          auto it = h->tc_w.find(Pp.seg[0].w);
+          if (it != h->tc_w.end()) { T.pf0 = it->second.first; T.pf1 = it->second.second; T.pf_bytes = (unsigned long long)C * C * 2; }
+        }
       } else {
         att = this->T(C, level); T.out = att.p;
       }

@@ -20,7 +20,22 @@ struct ApplyParams {
   int B; Geo geo;                                      // OUTPUT geometry
   void* hi; void* lo;                                  // __nv_bfloat16 [B][L][C0+C1]
   void* raw_hi; void* raw_lo;                          // optional: split of the UN-normalised (but resampled) input as well
+  // L2 prefetch of the consumer GEMM's (cold, HBM-resident) split weights while this short kernel runs
+  const void* pf0; const void* pf1; unsigned long long pf_bytes;
 };
+// each CTA prefetches one 16-byte-aligned slice of [p, p+bytes) into L2 (fire and forget)
+__device__ __forceinline__ void mtv_prefetch_slice(const void* p0, const void* p1, unsigned long long bytes, unsigned int cta,
+                                                   unsigned int nctas) {
+  if (!p0 || threadIdx.x != 0) return;
+  unsigned long long per = ((bytes + nctas - 1) / nctas + 15ull) & ~15ull;
+  const unsigned long long off = (unsigned long long)cta * per;
+  if (off >= bytes) return;
+  if (off + per > bytes) per = (bytes - off) & ~15ull;
+  if (!per) return;
+  const unsigned int sz = (unsigned int)per;
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"((const char*)p0 + off), "r"(sz) : "memory");
+  if (p1) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"((const char*)p1 + off), "r"(sz) : "memory");
+}
 
 // D[B*L][Cout] = sum_tap A_tap[B*L][Cin] * W[tap][Cout][Cin]^T   (+bias, +residual)
 struct TcConvParams {
@@ -56,6 +71,7 @@ struct AttnTcParams {
   CUtensorMap tmV_hi, tmV_lo;     // (L, B*H*D) box (64, D)
   float* out;                     // [B][L][C] fp32, or nullptr when out_hi / out_lo are given
   void* out_hi; void* out_lo;     // optional split-bf16 [B][L][C]: the A operand of the proj_out GEMM
+  const void* pf0; const void* pf1; unsigned long long pf_bytes;   // L2 prefetch of the proj_out weights
   int B, L, C, heads;
   int nseg; int seg_off[4];
 };
