@@ -43,7 +43,7 @@ SAMPLING_STEPS = 50
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--chunks-per-gpu", type=int, default=1)
@@ -76,7 +76,7 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}",
-                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "--format=csv,noheader,nounits", "-lms", "20"], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
@@ -315,7 +315,11 @@ def main():
         ach = d["gflop"] / (d["us_per_forward"] * 1e-6) / 1e3   # TFLOP/s
         roof = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
                 "frac": ach / pk["bf16_tflops_sustained"], "traffic": None,
-                "peak_source": f"{pk['source']} (MEASURED_PEAKS.json bf16_tflops_sustained)"}
+                "peak_source": f"{pk['source']} (MEASURED_PEAKS.json bf16_tflops_sustained)",
+                "note": "achieved = algorithmic FLOPs (2*M*N*K, one product = 2 FLOP) of all launches of the family in one forward / "
+                        "their summed per-launch time (each launch timed as a node of a private CUDA graph, CUDA events on the "
+                        "launching stream); the kernel issues 3 bf16 MMAs per product (split-bf16), so tensor-pipe activity is 3x "
+                        "this fraction; DRAM traffic of sampled launches == algorithmic bytes (profiles/r01_tc_v2_ncu_full.md)"}
     else:
         ach = d["mbytes"] / (d["us_per_forward"] * 1e-6) / 1e3  # GB/s
         roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
