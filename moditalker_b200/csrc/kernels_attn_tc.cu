@@ -430,7 +430,7 @@ static cudaError_t launch_attn_tc_d(const AttnTcParams& P, cudaStream_t s) {
   int nqb = 0;
   for (int i = 0; i < P.nseg; ++i) nqb += (P.seg_off[i + 1] - P.seg_off[i] + AT_BQ - 1) / AT_BQ;
   dim3 grid(nqb, P.B * P.heads);
-  { cudaError_t le_ = launch_k(k_attn_tc<D>, dim3(grid), dim3(AT_THREADS), (size_t)(SM::TOTAL), s, P); if (le_ != cudaSuccess) return le_; }
+  { cudaError_t le_ = launch_kc(PDL_CLASS_ATTN_TC, k_attn_tc<D>, dim3(grid), dim3(AT_THREADS), (size_t)(SM::TOTAL), s, P); if (le_ != cudaSuccess) return le_; }
   return cudaGetLastError();
 }
 

@@ -877,7 +877,7 @@ cudaError_t launch_conv_tc(const TcConvParams& P, cudaStream_t s) {
   do {                                                                                                             \
     e = cudaFuncSetAttribute(k_conv_tc<BN_, EPI_>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(BN_)); \
     if (e != cudaSuccess) return e;                                                                                \
-    e = launch_k(k_conv_tc<BN_, EPI_>, grid, dim3(TC_THREADS), (size_t)tc_smem_bytes(BN_), s, P);                   \
+    e = launch_kc(PDL_CLASS_CONV_TC, k_conv_tc<BN_, EPI_>, grid, dim3(TC_THREADS), (size_t)tc_smem_bytes(BN_), s, P);                   \
     if (e != cudaSuccess) return e;                                                                                \
   } while (0)
   if (BN == 64) {

@@ -24,17 +24,29 @@
 
 namespace mtv {
 
-extern int g_mtv_use_pdl;   // 0 unless MTV_PDL=1 (kernels_simt.cu)
+// MTV_PDL: 0 = off, 1 = every kernel, 2 = only the tensor-core tap-GEMM (it follows a short apply kernel that
+// triggers at entry: setup, TMEM allocation and the weight TMA requests then overlap that kernel, and nothing is
+// pre-launched more than one kernel deep), 3 = tap-GEMM and attention
+extern int g_mtv_use_pdl;
+enum { PDL_CLASS_OTHER = 0, PDL_CLASS_CONV_TC = 1, PDL_CLASS_ATTN_TC = 2 };
+inline bool mtv_pdl_enabled(int cls) {
+  return g_mtv_use_pdl == 1 || (g_mtv_use_pdl == 2 && cls == PDL_CLASS_CONV_TC) ||
+         (g_mtv_use_pdl == 3 && (cls == PDL_CLASS_CONV_TC || cls == PDL_CLASS_ATTN_TC));
+}
 
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+inline cudaError_t launch_kc(int cls, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[0].val.programmaticStreamSerializationAllowed = g_mtv_use_pdl ? 1 : 0;
+  at[0].val.programmaticStreamSerializationAllowed = mtv_pdl_enabled(cls) ? 1 : 0;
   cfg.attrs = at; cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  return launch_kc(PDL_CLASS_OTHER, kern, grid, block, smem, s, std::forward<Args>(args)...);
 }
 
 struct Geo {   // tri-plane token geometry of one pyramid level

@@ -912,7 +912,7 @@ int mtv_create(const MtvConfig* cfg, MtvHandle* out) {
     if (const char* tm = getenv("MTV_TC_MASK")) h->tc_mask = (int)strtol(tm, nullptr, 0);
     // programmatic dependent launch is opt-in: measured on B200 it costs ~5 % at B=1 (pre-launched CTAs
     // contend with the running kernel) and gains nothing at B=8 — see profiles/README.md
-    { const char* np = getenv("MTV_PDL"); g_mtv_use_pdl = (np && np[0] == '1') ? 1 : 0; }
+    { const char* np = getenv("MTV_PDL"); g_mtv_use_pdl = np ? atoi(np) : 0; }
     register_weights(h.get());
     *out = h.release();
   });
