@@ -221,11 +221,11 @@ cudaError_t launch_apply_split(const ApplyParams& P, cudaStream_t s) {
     const int maxp = P.geo.res * P.geo.res;
     dim3 grid((maxp + P.chunk_tokens - 1) / P.chunk_tokens, 3, P.B);
     const size_t smem = (size_t)C * 2 * sizeof(float);
-    { cudaError_t le_ = launch_k(k_apply_norm_split, dim3(grid), dim3(256), (size_t)(smem), s, P); if (le_ != cudaSuccess) return le_; }
+    { cudaError_t le_ = launch_kc(PDL_CLASS_APPLY, k_apply_norm_split, dim3(grid), dim3(256), (size_t)(smem), s, P); if (le_ != cudaSuccess) return le_; }
     return cudaGetLastError();
   }
   const size_t total = (size_t)P.B * P.geo.L * ((P.C0 + P.C1) / 4);
-  { cudaError_t le_ = launch_k(k_apply_split, dim3((unsigned)((total + 255) / 256)), dim3(256), (size_t)(0), s, P); if (le_ != cudaSuccess) return le_; }
+  { cudaError_t le_ = launch_kc(PDL_CLASS_APPLY, k_apply_split, dim3((unsigned)((total + 255) / 256)), dim3(256), (size_t)(0), s, P); if (le_ != cudaSuccess) return le_; }
   return cudaGetLastError();
 }
 
@@ -892,7 +892,7 @@ cudaError_t launch_conv_tc(const TcConvParams& P, cudaStream_t s) {
   if (e != cudaSuccess) return e;
   if (P.ksplit > 1) {
     dim3 rgrid(M / 32, P.Cout / 32);
-    { cudaError_t le_ = launch_k(k_tc_splitk_epilogue, dim3(rgrid), dim3(256), (size_t)(0), s, P); if (le_ != cudaSuccess) return le_; }
+    { cudaError_t le_ = launch_kc(PDL_CLASS_REDUCE, k_tc_splitk_epilogue, dim3(rgrid), dim3(256), (size_t)(0), s, P); if (le_ != cudaSuccess) return le_; }
     e = cudaGetLastError();
   }
   return e;

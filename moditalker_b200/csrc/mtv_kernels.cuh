@@ -24,15 +24,13 @@
 
 namespace mtv {
 
-// MTV_PDL: 0 = off, 1 = every kernel, 2 = only the tensor-core tap-GEMM (it follows a short apply kernel that
-// triggers at entry: setup, TMEM allocation and the weight TMA requests then overlap that kernel, and nothing is
-// pre-launched more than one kernel deep), 3 = tap-GEMM and attention
+// MTV_PDL is a bit mask of kernel classes launched with programmatic stream serialisation (default 1):
+//   1 tensor-core tap-GEMM (follows a short apply kernel that triggers at entry: setup, TMEM allocation and the
+//     weight TMA requests overlap that kernel, nothing is pre-launched more than one kernel deep)
+//   2 tensor-core attention, 4 apply kernels, 8 split-K reductions, 16 everything else
 extern int g_mtv_use_pdl;
-enum { PDL_CLASS_OTHER = 0, PDL_CLASS_CONV_TC = 1, PDL_CLASS_ATTN_TC = 2 };
-inline bool mtv_pdl_enabled(int cls) {
-  return g_mtv_use_pdl == 1 || (g_mtv_use_pdl == 2 && cls == PDL_CLASS_CONV_TC) ||
-         (g_mtv_use_pdl == 3 && (cls == PDL_CLASS_CONV_TC || cls == PDL_CLASS_ATTN_TC));
-}
+enum { PDL_CLASS_CONV_TC = 1, PDL_CLASS_ATTN_TC = 2, PDL_CLASS_APPLY = 4, PDL_CLASS_REDUCE = 8, PDL_CLASS_OTHER = 16 };
+inline bool mtv_pdl_enabled(int cls) { return (g_mtv_use_pdl & cls) != 0; }
 
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_kc(int cls, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {

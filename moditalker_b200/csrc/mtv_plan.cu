@@ -910,9 +910,10 @@ int mtv_create(const MtvConfig* cfg, MtvHandle* out) {
     const char* ng = getenv("MTV_NO_GRAPH");
     h->use_graph = !(ng && ng[0] == '1');
     if (const char* tm = getenv("MTV_TC_MASK")) h->tc_mask = (int)strtol(tm, nullptr, 0);
-    // programmatic dependent launch is opt-in: measured on B200 it costs ~5 % at B=1 (pre-launched CTAs
-    // contend with the running kernel) and gains nothing at B=8 — see profiles/README.md
-    { const char* np = getenv("MTV_PDL"); g_mtv_use_pdl = np ? atoi(np) : 0; }
+    // programmatic dependent launch, by kernel class (mtv_kernels.cuh).  Default: only the tensor-core tap-GEMM
+    // (measured on B200: -7.6 % step time at B=1, -3 % at B=8; enabling it for every kernel is a net loss because
+    // kernels pre-launched several deep contend with the running one)
+    { const char* np = getenv("MTV_PDL"); g_mtv_use_pdl = np ? atoi(np) : 1; }
     register_weights(h.get());
     *out = h.release();
   });

@@ -48,7 +48,7 @@ def main():
         cases = (("verified 0x1ff, no PDL", 0x1ff), ("verified 0x1ff + PDL", 0x1ff), ("+fused launches, no PDL", 0x3ff),
                  ("all (0x3ff + PDL)", 0x3ff))
     for name, mask in cases:
-        os.environ["MTV_PDL"] = "0" if "no PDL" in name else "1"
+        os.environ["MTV_PDL"] = "0" if "no PDL" in name else "31"
         try:
             m = make(cfg, 0, mask)
             with torch.no_grad():
