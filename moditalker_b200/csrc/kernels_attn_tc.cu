@@ -104,9 +104,16 @@ __device__ __forceinline__ void a_tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
 }
 __device__ __forceinline__ void a_tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
-  const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<const uint32_t*>(&v);
+// two floats -> packed bf16x2 (e0 in the low half = lower address), one instruction
+__device__ __forceinline__ uint32_t cvt_bf16x2(float e0, float e1) {
+  uint32_t d;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(e1), "f"(e0));
+  return d;
+}
+__device__ __forceinline__ float ex2_approx(float x) {   // 2^x, max rel. error 2^-22; 2^-inf = 0
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 
 }  // namespace
@@ -183,7 +190,7 @@ __global__ void __launch_bounds__(AT_THREADS, (D <= 32) ? 2 : 1) k_attn_tc(const
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_q, bar_full[AT_NS], bar_empty[AT_NS], bar_s_full, bar_s_free, bar_p_full, bar_o_full;
   __shared__ uint32_t tmem_base_s;
-  __shared__ float s_xchg[2][AT_BQ];      // per-row exchange between the two softmax halves (row max, final row sum)
+  __shared__ float s_xchg[2][2][AT_BQ];   // [block parity][half][row]: row max (and the final row sum) exchange
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem0 = (a_smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -330,30 +337,37 @@ __global__ void __launch_bounds__(AT_THREADS, (D <= 32) ? 2 : 1) k_attn_tc(const
       }
       a_fence_before();
       a_mbar_arrive(&bar_s_free);                           // S TMEM may be overwritten by S(j+1)
-      const int valid = min(32, len - j * AT_BKV - half * 32);   // may be <= 0 for the upper half of a short tail
-      float mx = -INFINITY;
+      const int valid = len - j * AT_BKV - half * 32;       // >= 32 except in the last block (may be <= 0 there)
+      if (valid < 32) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) { if (i >= valid) s[i] = -INFINITY; mx = fmaxf(mx, s[i]); }
+        for (int i = 0; i < 32; ++i) if (i >= valid) s[i] = -INFINITY;
+      }
+      float mx = fmaxf(s[0], s[1]);
+#pragma unroll
+      for (int i = 2; i < 32; ++i) mx = fmaxf(mx, s[i]);
       // row max over both halves
-      s_xchg[half][row] = mx;
+      s_xchg[j & 1][half][row] = mx;
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      mx = fmaxf(mx, s_xchg[half ^ 1][row]);
+      mx = fmaxf(mx, s_xchg[j & 1][half ^ 1][row]);
       const float m_new = fmaxf(m_run, mx);                 // finite: the lower half always holds a valid key
-      const float corr = exp2f(m_run - m_new);
-      float sum = 0.f;
+      const float corr = ex2_approx(m_run - m_new);
+      float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) { s[i] = exp2f(s[i] - m_new); sum += s[i]; }
+      for (int i = 0; i < 32; i += 2) {
+        s[i] = ex2_approx(s[i] - m_new); s[i + 1] = ex2_approx(s[i + 1] - m_new);
+        sum0 += s[i]; sum1 += s[i + 1];
+      }
       if (j > 0) {                                          // O block (j-1) finished -> fold it in before rescaling
         a_mbar_wait(&bar_o_full, (uint32_t)((j - 1) & 1));
         a_fence_after();
         fold_O();
       }
-      l_part = l_part * corr + sum;
+      l_part = l_part * corr + (sum0 + sum1);
       m_run = m_new;
 #pragma unroll
       for (int d = 0; d < DH; ++d) o[d] *= corr;
       // P(j) -> smem, split bf16, 128B-swizzled K-major rows (16-byte chunk c of row r at c ^ (r & 7));
-      // this half owns chunks [4*half, 4*half + 4)
+      // this half owns chunks [4*half, 4*half + 4).  hi = bf16x2(p), lo = bf16x2(p - float(hi)): 3 instr / element
       {
         const uint32_t rbase_hi = sP_hi + (uint32_t)row * 128u, rbase_lo = sP_lo + (uint32_t)row * 128u;
 #pragma unroll
@@ -362,9 +376,8 @@ __global__ void __launch_bounds__(AT_THREADS, (D <= 32) ? 2 : 1) k_attn_tc(const
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const float p0 = s[c * 8 + 2 * e], p1 = s[c * 8 + 2 * e + 1];
-            const __nv_bfloat16 h0 = __float2bfloat16_rn(p0), h1 = __float2bfloat16_rn(p1);
-            hi[e] = pack_bf16(__bfloat162float(h0), __bfloat162float(h1));
-            lo[e] = pack_bf16(p0 - __bfloat162float(h0), p1 - __bfloat162float(h1));
+            hi[e] = cvt_bf16x2(p0, p1);
+            lo[e] = cvt_bf16x2(p0 - __uint_as_float(hi[e] << 16), p1 - __uint_as_float(hi[e] & 0xffff0000u));
           }
           const uint32_t off = (uint32_t)((((half << 2) | c) ^ (row & 7)) * 16);
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rbase_hi + off), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
@@ -374,19 +387,18 @@ __global__ void __launch_bounds__(AT_THREADS, (D <= 32) ? 2 : 1) k_attn_tc(const
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA (async proxy)
       a_fence_before();
       a_mbar_arrive(&bar_p_full);
-      // the exchange slots are rewritten next block: everyone has read them once this barrier-protected
-      // point is passed by both halves (the next write happens after the next bar_s_full wait + tcgen05.ld,
-      // and the partner's read above precedes its arrive on bar_p_full, which precedes S(j+1)... keep it simple:
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      // s_xchg is double-buffered by block parity: slot (j & 1) is rewritten in block j + 2, i.e. after the
+      // bar.sync of block j + 1, which every reader of block j has passed by then
     }
     a_mbar_wait(&bar_o_full, (uint32_t)((nblk - 1) & 1));
     MTV_PDL_TRIGGER();
     a_fence_after();
     fold_O();
     // total row sum = both halves' partial sums
-    s_xchg[half][row] = l_part;
+    asm volatile("bar.sync 1, 256;" ::: "memory");          // all max-exchange reads done before the slots are reused
+    s_xchg[0][half][row] = l_part;
     asm volatile("bar.sync 1, 256;" ::: "memory");
-    const float l_run = l_part + s_xchg[half ^ 1][row];
+    const float l_run = l_part + s_xchg[0][half ^ 1][row];
     const int q = q0 + row;
     if (q < len) {
       const int b = bh / P.heads, h = bh - b * P.heads;
