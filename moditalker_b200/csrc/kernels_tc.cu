@@ -322,6 +322,17 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -510,7 +521,12 @@ template <int BN, int EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant__ TcConvParams P) {
   constexpr int NS = tc_stages(BN);
   constexpr int STAGE = tc_stage_bytes(BN);
+  // Stacked-N: W_hi and W_lo tiles are adjacent in smem, so ONE MMA with N = 2*BN computes
+  // [A_hi*W_hi | A_hi*W_lo] into TMEM columns [0,BN) | [BN,2BN) and a second one adds A_lo*W_hi into [0,BN):
+  // two MMAs and 14 KB of operand reads per k-step instead of three and 18 KB (the main loop is
+  // shared-memory-bandwidth bound); the epilogue sums the two column groups.
   constexpr uint32_t IDESC = umma_idesc_bf16(TC_BM, BN);
+  constexpr uint32_t IDESC2 = umma_idesc_bf16(TC_BM, 2 * BN);
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_full[NS], bar_empty[NS], bar_acc;
   __shared__ uint32_t tmem_base_s;
@@ -545,7 +561,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
     prefetch_tmap(&P.tmA_hi[0]); prefetch_tmap(&P.tmA_lo[0]); prefetch_tmap(&P.tmW_hi); prefetch_tmap(&P.tmW_lo);
   }
   if (warp == 1) {   // TMEM: BN fp32 accumulator columns x 128 lanes
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"((uint32_t)BN) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"((uint32_t)(2 * BN)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -619,10 +635,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
 #pragma unroll
         for (int k = 0; k < TC_BK / 16; ++k) {
           const uint64_t a_hi = umma_desc_sw128(sA_hi + k * 32), a_lo = umma_desc_sw128(sA_lo + k * 32);
-          const uint64_t w_hi = umma_desc_sw128(sW_hi + k * 32), w_lo = umma_desc_sw128(sW_lo + k * 32);
-          umma_bf16(tmem_base, a_hi, w_hi, IDESC, (it > it0 || k > 0) ? 1u : 0u);
+          const uint64_t w_hi = umma_desc_sw128(sW_hi + k * 32);          // rows [0,BN) = W_hi, [BN,2BN) = W_lo
+          umma_bf16(tmem_base, a_hi, w_hi, IDESC2, (it > it0 || k > 0) ? 1u : 0u);
           umma_bf16(tmem_base, a_lo, w_hi, IDESC, 1u);
-          umma_bf16(tmem_base, a_hi, w_lo, IDESC, 1u);
         }
         umma_commit(&bar_empty[stage]);          // frees the smem slot once these MMAs have read it
         if (++stage == NS) { stage = 0; phase ^= 1u; }
@@ -664,7 +679,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
     for (int c0 = 0; c0 < BN; c0 += 32) {
       uint32_t r[32];
       __syncwarp();
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+      {
+        uint32_t r2[32];
+        tmem_ld32_nowait(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+        tmem_ld32_nowait(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(BN + c0), r2);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+      }
       const int n = n0 + c0;
       // the chunk's bias is fetched in one go: loads inside the store loop would serialise behind the
       // (possibly aliasing) stores and cost ~500 cycles each
@@ -780,7 +802,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * BN)) : "memory");
   }
   if (dbg && threadIdx.x == 0) {
     const unsigned int slot = atomicAdd(&g_tc_dbg_count, 1u);
