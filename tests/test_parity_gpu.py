@@ -151,6 +151,29 @@ def test_eager_capture_replay_are_bit_identical():
     assert torch.equal(a, b)
 
 
+def test_launch_modes_do_not_change_results(monkeypatch):
+    """Programmatic dependent launch (any class mask) and the launch fusions only reorder / overlap work:
+    outputs must be bit-identical to the plain serial plan."""
+    cfg = config_by_name("tiny")
+    x, cond, ic, t = synth_inputs(2, seed=88, t=[5, 900])
+    outs = {}
+    for name, env in (("pdl default", {}), ("pdl off", {"MTV_PDL": "0"}), ("pdl all", {"MTV_PDL": "31"}),
+                      ("no graph", {"MTV_NO_GRAPH": "1"})):
+        for k in ("MTV_PDL", "MTV_NO_GRAPH"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        m = DiffusionWrapper(UNetModel(**cfg))
+        m.load_state_dict(synth_state_dict(cfg, 0, "diffusion_model."), strict=True)
+        m = m.to(DEV).eval()
+        for _ in range(3):                       # eager, capture, replay
+            outs[name] = run(m, x, cond, ic, t)
+        del m
+    ref = outs["pdl off"]
+    for name, o in outs.items():
+        assert torch.equal(o, ref), f"{name} differs from the serial plan"
+
+
 def test_batch_independence_full_config():
     """Nothing in the UNet mixes samples (GroupNorm is per sample, attention per
     sample): a batch equals its samples run alone, up to split-K summation order."""
