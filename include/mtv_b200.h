@@ -51,8 +51,9 @@ typedef struct MtvConfig {
   int32_t channel_mult[MTV_MAX_LEVELS];
   int32_t attn_at_level[MTV_MAX_LEVELS]; /* 1 if (1<<level) is in attention_resolutions */
   int32_t device;                 /* CUDA device ordinal */
-  int32_t kernel_path;            /* 0 = default (tcgen05 where a tile shape exists, SIMT CUDA elsewhere),
-                                     1 = force the fp32 SIMT CUDA kernels everywhere (debug / cross-check) */
+  int32_t kernel_path;            /* 0 = default: tcgen05 tensor-core kernels (split-bf16, ~1e-5 vs fp32) for every
+                                         tap-GEMM and attention with a tile shape, fp32 CUDA-core kernels for stem / head,
+                                     1 = fp32 CUDA-core kernels everywhere (cross-check path of the tests, ~1e-6) */
 } MtvConfig;
 
 int  mtv_abi_version(void);

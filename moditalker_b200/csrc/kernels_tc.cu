@@ -10,11 +10,13 @@
 //                   token-major activation (one shifted box per tap; the conv's zero padding is
 //                   TMA out-of-bounds fill, so planes never bleed into each other), W tiles are
 //                   TMA boxes of the pre-split weights.  fp32-class accuracy from three bf16
-//                   MMAs per product:  A_hi*W_hi + A_lo*W_hi + A_hi*W_lo  (error ~2^-16 per
+//                   products per product:  A_hi*W_hi + A_lo*W_hi + A_hi*W_lo  (error ~2^-16 per
 //                   product instead of bf16's 2^-8; the MToV parity bar of 1e-3 rules out plain
 //                   bf16 and leaves single-pass TF32 no margin over a 50-step trajectory,
-//                   SURVEY.md §7).  Warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer
-//                   (+TMEM alloc), warps 2-5 = epilogue (tcgen05.ld -> +bias +residual -> HBM).
+//                   SURVEY.md §7), issued as two MMAs per k-step (stacked N: [W_hi; W_lo]).
+//                   Warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc),
+//                   warps 2-5 = epilogue (tcgen05.ld -> +bias +residual [+GroupNorm sums | qkv
+//                   operand split] -> HBM), specialised at compile time (EPI).
 //
 // Reference semantics: ResBlock._forward conv3x3s (unet.py:134,159,178-207), the 1x1
 // qkv / proj_out convs of AttentionBlock* (unet.py:234,242,251-254,297-300).
@@ -631,7 +633,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
         if (dbg && it == it1 - 1) s_stamp[4] = clock64();           // last operands landed
         tc_fence_after();
         const uint32_t sA_hi = smem0 + stage * STAGE, sA_lo = sA_hi + TC_BM * 128;
-        const uint32_t sW_hi = sA_lo + TC_BM * 128, sW_lo = sW_hi + BN * 128;
+        const uint32_t sW_hi = sA_lo + TC_BM * 128;
 #pragma unroll
         for (int k = 0; k < TC_BK / 16; ++k) {
           const uint64_t a_hi = umma_desc_sw128(sA_hi + k * 32), a_lo = umma_desc_sw128(sA_lo + k * 32);
