@@ -160,7 +160,7 @@ struct MtvHandle_t {
   std::map<int, std::unique_ptr<Plan>> plans;
   Plan* last_plan = nullptr;
   int64_t weight_bytes = 0;
-  int tc_mask = 0x7ff;
+  int tc_mask = 0xfff;
   cudaStream_t cap_stream = nullptr;
   cudaStream_t capture_stream() {
     if (!cap_stream) CK(cudaStreamCreateWithFlags(&cap_stream, cudaStreamNonBlocking));
@@ -170,10 +170,38 @@ struct MtvHandle_t {
   float* dalloc(size_t bytes) {
     void* p = nullptr; CK(cudaMalloc(&p, bytes)); allocs.push_back(p); return (float*)p;
   }
+  // Small, reused-every-step tensors (biases, GroupNorm affines, the per-step FiLM table) live in one arena
+  // that is marked L2-persisting for every kernel of the forward: read once per step, they would otherwise be
+  // evicted by the 529 MB weight stream and cost a DRAM miss on the critical path of each short kernel.
+  char* small_arena = nullptr; size_t small_cap = 0, small_used = 0;
+  float* small_alloc(size_t bytes) {
+    if (!small_arena) { small_cap = 8u << 20; small_arena = (char*)dalloc(small_cap); }
+    const size_t b = (bytes + 255) & ~(size_t)255;
+    if (small_used + b > small_cap) return nullptr;
+    float* p = (float*)(small_arena + small_used); small_used += b; return p;
+  }
+  std::map<cudaStream_t, bool> l2_window_set;
+  void apply_l2_window(cudaStream_t s) {
+    if (!small_arena || !small_used || l2_window_set.count(s)) return;
+    static bool limit_set = false;
+    if (!limit_set) { cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, small_cap); limit_set = true; }
+    cudaStreamAttrValue attr; memset(&attr, 0, sizeof(attr));
+    attr.accessPolicyWindow.base_ptr = small_arena;
+    attr.accessPolicyWindow.num_bytes = small_used;
+    attr.accessPolicyWindow.hitRatio = 1.0f;
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    if (cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess) cudaGetLastError();
+    l2_window_set[s] = true;
+  }
   int add_weight(const std::string& name, std::vector<int64_t> shape, int kind, float* view = nullptr) {
     Weight w; w.name = name; w.shape = shape; w.kind = kind; w.elems = 1;
     for (auto d : shape) w.elems *= (size_t)d;
-    if (view) { w.dev = view; w.owned = false; } else { w.dev = dalloc(w.elems * sizeof(float)); }
+    if (view) { w.dev = view; w.owned = false; }
+    else {
+      w.dev = (shape.size() == 1 && ((tc_mask >> 11) & 1)) ? small_alloc(w.elems * sizeof(float)) : nullptr;
+      if (!w.dev) w.dev = dalloc(w.elems * sizeof(float));
+    }
     if (kind == WK_CONV && cfg.kernel_path != 1 && shape[0] % 64 == 0 && shape[1] % 64 == 0) {
       w.hi = dalloc(w.elems * 2); w.lo = dalloc(w.elems * 2);
       tc_w[w.dev] = std::make_pair(w.hi, w.lo);
@@ -752,7 +780,8 @@ struct Builder {
       };
       pl->ops.push_back(op);
     }
-    film_buf = (float*)dalloc((size_t)B * A.J * sizeof(float));
+    film_buf = ((h->tc_mask >> 11) & 1) ? h->small_alloc((size_t)B * A.J * sizeof(float)) : nullptr;
+    if (!film_buf) film_buf = (float*)dalloc((size_t)B * A.J * sizeof(float));
     {
       EmbParams P{}; P.t = t_buf; P.B = B; P.mc = mc; P.ted = ted; P.freqs = h->freqs;
       P.w1 = h->W("time_embed.0.weight"); P.b1 = h->W("time_embed.0.bias");
@@ -840,6 +869,7 @@ void forward(MtvHandle_t* h, const RunCtx& ctx, int B, cudaStream_t s) {
   ensure_ready(h, s);
   Plan* pl = get_plan(h, B);
   pl->ctx = ctx;
+  h->apply_l2_window(s);
   run_ops(pl, 0, s);
   if (!h->use_graph) {
     run_ops(pl, 1, s);
@@ -851,6 +881,7 @@ void forward(MtvHandle_t* h, const RunCtx& ctx, int B, cudaStream_t s) {
         // capture on a private stream: the caller's stream may be the legacy default stream,
         // which cannot be captured
         cudaStream_t cs = h->capture_stream();
+        h->apply_l2_window(cs);      // kernel nodes inherit the capturing stream's access-policy window
         CK(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
         try { run_ops(pl, 1, cs); } catch (...) { cudaGraph_t g = nullptr; cudaStreamEndCapture(cs, &g); if (g) cudaGraphDestroy(g); throw; }
         CK(cudaStreamEndCapture(cs, &pl->graph));
