@@ -445,7 +445,9 @@ struct Builder {
         A.csum0 = n.x0.csum; A.csum1 = n.has_x1 ? n.x1.csum : nullptr;
         A.gamma = n.gamma; A.beta = n.beta; A.joint = n.joint ? 1 : 0;
         if (n.film_off >= 0) { A.film = film_buf + n.film_off; A.film_stride = h->arch.J; }
-        A.chunk_tokens = g.res * g.res >= 256 ? 16 : 8;
+        // <= 2 work items (4 channels of one token) per thread: the item loop is a serial chain of L2 round trips,
+        // so small levels with many channels get more, smaller CTAs rather than long loops in a handful of CTAs
+        A.chunk_tokens = std::max(1, std::min(16, 2048 / C));
       } else {
         const NormRef r = materialize(norm_id);
         A.nrm_a = r.a; A.nrm_d = r.d; A.nrm_nseg = r.nseg;
