@@ -124,6 +124,39 @@ __global__ void __launch_bounds__(256) k_apply_norm_split(const __grid_constant_
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const Geo gs = P.resample == RS_NONE ? g : (P.resample == RS_UP2 ? geo_down(g) : geo_up(g));
   const double cnt = (double)cpg * (P.joint ? (double)gs.L : (double)(p == 0 ? gs.res * gs.res : gs.t * gs.res));
+  const int cq = C >> 2;
+  const int poff = tc_plane_off(g, p);
+  const int total = (t1 - t0) * cq;
+  // item = 4 channels of one token.  Two items per trip with both loads issued before either is
+  // consumed: the loop is a chain of L2 round trips, not arithmetic.
+  struct Item { const float* q; size_t o; int c, Cs; bool ok; };
+  auto locate = [&](int idx) {
+    Item it; it.ok = idx < total;
+    const int id = it.ok ? idx : 0;
+    const int tl = t0 + id / cq; it.c = (id % cq) * 4;
+    const int y = tl / g.res, x = tl - y * g.res;
+    const float* src; int cc;
+    if (it.c < P.C0) { src = P.src0; it.Cs = P.C0; cc = it.c; } else { src = P.src1; it.Cs = P.C1; cc = it.c - P.C0; }
+    int ts = poff + tl;
+    if (P.resample == RS_UP2) ts = tc_plane_off(gs, p) + (y >> 1) * gs.res + (x >> 1);
+    else if (P.resample == RS_DOWN2) ts = tc_plane_off(gs, p) + (2 * y) * gs.res + 2 * x;
+    it.q = src + ((size_t)b * gs.L + ts) * it.Cs + cc;
+    it.o = ((size_t)b * g.L + poff + tl) * C + it.c;
+    return it;
+  };
+  auto fetch = [&](const Item& it, float4& w0, float4& w1, float4& w2, float4& w3) {
+    if (!it.ok) return;
+    w0 = __ldg(reinterpret_cast<const float4*>(it.q));
+    if (P.resample == RS_DOWN2) {
+      w1 = __ldg(reinterpret_cast<const float4*>(it.q + it.Cs));
+      w2 = __ldg(reinterpret_cast<const float4*>(it.q + (size_t)gs.res * it.Cs));
+      w3 = __ldg(reinterpret_cast<const float4*>(it.q + (size_t)(gs.res + 1) * it.Cs));
+    }
+  };
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  Item i0 = locate(tid), i1 = locate(tid + 256);
+  float4 a0 = z4, a1 = z4, a2 = z4, a3 = z4, b0 = z4, b1 = z4, b2 = z4, b3 = z4;
+  fetch(i0, a0, a1, a2, a3); fetch(i1, b0, b1, b2, b3);   // first trip's activations: in flight under the statistics pass
   // gamma / beta / FiLM rows are read once per step and have left L2 by then: issue their (DRAM-latency)
   // loads first so they overlap the statistics pass instead of following it
   float pg[8], pb[8], psc[8], psh[8];
@@ -175,45 +208,36 @@ __global__ void __launch_bounds__(256) k_apply_norm_split(const __grid_constant_
       sa[c] = (float)a; sd[c] = (float)d;
     }
   }
-  __syncthreads();
-  const int cq = C >> 2;
-  const int poff = tc_plane_off(g, p);
-  const int total = (t1 - t0) * cq;
-  for (int idx = tid; idx < total; idx += 256) {
-    const int tl = t0 + idx / cq, c = (idx % cq) * 4;
-    const int y = tl / g.res, x = tl - y * g.res;
-    const int tok = poff + tl;
-    const float* src; int Cs, cc;
-    if (c < P.C0) { src = P.src0; Cs = P.C0; cc = c; } else { src = P.src1; Cs = P.C1; cc = c - P.C0; }
-    const float4 na = *reinterpret_cast<const float4*>(sa + c), nd = *reinterpret_cast<const float4*>(sd + c);
+  auto finish = [&](const Item& it, const float4 w0, const float4 w1, const float4 w2, const float4 w3) {
+    const float4 na = *reinterpret_cast<const float4*>(sa + it.c), nd = *reinterpret_cast<const float4*>(sd + it.c);
     auto xf = [&](float4 v) {
       v.x = fmaf(v.x, na.x, nd.x); v.y = fmaf(v.y, na.y, nd.y); v.z = fmaf(v.z, na.z, nd.z); v.w = fmaf(v.w, na.w, nd.w);
       if (P.silu) { v.x = silu_tc(v.x); v.y = silu_tc(v.y); v.z = silu_tc(v.z); v.w = silu_tc(v.w); }
       return v;
     };
     float4 v, rw;
-    if (P.resample == RS_NONE) {
-      rw = __ldg(reinterpret_cast<const float4*>(src + ((size_t)b * g.L + tok) * Cs + cc));
-      v = xf(rw);
-    } else if (P.resample == RS_UP2) {
-      const int ts = tc_plane_off(gs, p) + (y >> 1) * gs.res + (x >> 1);
-      rw = __ldg(reinterpret_cast<const float4*>(src + ((size_t)b * gs.L + ts) * Cs + cc));
-      v = xf(rw);
+    if (P.resample != RS_DOWN2) {
+      rw = w0; v = xf(w0);
     } else {
-      const int ts = tc_plane_off(gs, p) + (2 * y) * gs.res + 2 * x;
-      const float* q = src + ((size_t)b * gs.L + ts) * Cs + cc;
-      const float4 w0 = __ldg(reinterpret_cast<const float4*>(q)), w1 = __ldg(reinterpret_cast<const float4*>(q + Cs));
-      const float4 w2 = __ldg(reinterpret_cast<const float4*>(q + (size_t)gs.res * Cs));
-      const float4 w3 = __ldg(reinterpret_cast<const float4*>(q + (size_t)(gs.res + 1) * Cs));
       const float4 v0 = xf(w0), v1 = xf(w1), v2 = xf(w2), v3 = xf(w3);
       v.x = 0.25f * ((v0.x + v1.x) + (v2.x + v3.x)); v.y = 0.25f * ((v0.y + v1.y) + (v2.y + v3.y));
       v.z = 0.25f * ((v0.z + v1.z) + (v2.z + v3.z)); v.w = 0.25f * ((v0.w + v1.w) + (v2.w + v3.w));
       rw.x = 0.25f * ((w0.x + w1.x) + (w2.x + w3.x)); rw.y = 0.25f * ((w0.y + w1.y) + (w2.y + w3.y));
       rw.z = 0.25f * ((w0.z + w1.z) + (w2.z + w3.z)); rw.w = 0.25f * ((w0.w + w1.w) + (w2.w + w3.w));
     }
-    const size_t o = ((size_t)b * g.L + tok) * C + c;
-    tc_store_split(v, P.hi, P.lo, o);
-    if (P.raw_hi) tc_store_split(rw, P.raw_hi, P.raw_lo, o);
+    tc_store_split(v, P.hi, P.lo, it.o);
+    if (P.raw_hi) tc_store_split(rw, P.raw_hi, P.raw_lo, it.o);
+  };
+  __syncthreads();
+  for (int idx = tid; idx < total; idx += 512) {
+    const Item c0 = i0, c1 = i1;
+    const float4 x0 = a0, x1 = a1, x2 = a2, x3 = a3, y0 = b0, y1 = b1, y2 = b2, y3 = b3;
+    if (idx + 512 < total) {                       // next trip's loads go out before this trip's math
+      i0 = locate(idx + 512); i1 = locate(idx + 768);
+      fetch(i0, a0, a1, a2, a3); fetch(i1, b0, b1, b2, b3);
+    }
+    finish(c0, x0, x1, x2, x3);
+    if (c1.ok) finish(c1, y0, y1, y2, y3);
   }
 }
 

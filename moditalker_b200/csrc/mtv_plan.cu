@@ -447,7 +447,13 @@ struct Builder {
         if (n.film_off >= 0) { A.film = film_buf + n.film_off; A.film_stride = h->arch.J; }
         // <= 2 work items (4 channels of one token) per thread: the item loop is a serial chain of L2 round trips,
         // so small levels with many channels get more, smaller CTAs rather than long loops in a handful of CTAs
-        A.chunk_tokens = std::max(1, std::min(16, 2048 / C));
+        {
+          const int floor_chunk = std::max(1, std::min(16, 2048 / C));
+          int chunk = g.res * g.res >= 256 ? 16 : 8;
+          auto ctas = [&](int ch) { return ((g.res * g.res + ch - 1) / ch) * 3 * B; };
+          while (chunk > floor_chunk && ctas(chunk) < 2 * h->num_sms) chunk >>= 1;   // enough CTAs already: keep the prologue amortised
+          A.chunk_tokens = chunk;
+        }
       } else {
         const NormRef r = materialize(norm_id);
         A.nrm_a = r.a; A.nrm_d = r.d; A.nrm_nseg = r.nseg;
