@@ -102,23 +102,14 @@ __global__ void __launch_bounds__(256) k_apply_split(const __grid_constant__ App
   if (P.raw_hi) tc_store_split(rw, P.raw_hi, P.raw_lo, o);
 }
 
-// GroupNorm32 finalise + apply in ONE kernel: group statistics come from the per-channel sums the
-// producing tap-GEMM accumulated in its epilogue (csum[b][plane][c][2], fp64), so no separate
-// statistics pass reads the activation again.  CTA = (token chunk, plane, sample); prologue turns
-// the sums of that (sample, plane | all planes) into the per-channel affine in shared memory
-// (FiLM folded in), then the body is k_apply_split's.
-__global__ void __launch_bounds__(256) k_apply_norm_split(const __grid_constant__ ApplyParams P) {
-  MTV_PDL_TRIGGER();
-  mtv_prefetch_slice(P.pf0, P.pf1, P.pf_bytes, blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z),
-                     gridDim.x * gridDim.y * gridDim.z);
-  MTV_PDL_WAIT();
-  extern __shared__ float s_aff[];                 // a[C] | d[C]
-  __shared__ double s_mean[32], s_rstd[32];
+// One work unit of the fused GroupNorm-finalise + apply: `chunk_tokens` tokens starting at chunk `chunk_idx` of plane p of
+// sample b, by a 256-thread CTA.  s_aff: 2*C floats, s_mean / s_rstd: 32 doubles each (all CTA-shared scratch).
+__device__ __forceinline__ void apply_norm_unit(const ApplyParams& P, float* s_aff, double* s_mean, double* s_rstd,
+                                                int chunk_idx, int p, int b) {
   const int C = P.C0 + P.C1, cpg = C / 32;
-  const int p = blockIdx.y, b = blockIdx.z;
   const Geo g = P.geo;
   const int plane_tokens = p == 0 ? g.res * g.res : g.t * g.res;
-  const int t0 = blockIdx.x * P.chunk_tokens;
+  const int t0 = chunk_idx * P.chunk_tokens;
   if (t0 >= plane_tokens) return;
   const int t1 = min(plane_tokens, t0 + P.chunk_tokens);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -241,6 +232,21 @@ __global__ void __launch_bounds__(256) k_apply_norm_split(const __grid_constant_
   }
 }
 
+// GroupNorm32 finalise + apply in ONE kernel: group statistics come from the per-channel sums the
+// producing tap-GEMM accumulated in its epilogue (csum[b][plane][c][2], fp64), so no separate
+// statistics pass reads the activation again.  CTA = (token chunk, plane, sample); prologue turns
+// the sums of that (sample, plane | all planes) into the per-channel affine in shared memory
+// (FiLM folded in), then the body is k_apply_split's.
+__global__ void __launch_bounds__(256) k_apply_norm_split(const __grid_constant__ ApplyParams P) {
+  MTV_PDL_TRIGGER();
+  mtv_prefetch_slice(P.pf0, P.pf1, P.pf_bytes, blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z),
+                     gridDim.x * gridDim.y * gridDim.z);
+  MTV_PDL_WAIT();
+  extern __shared__ float s_aff[];                 // a[C] | d[C]
+  __shared__ double s_mean[32], s_rstd[32];
+  apply_norm_unit(P, s_aff, s_mean, s_rstd, (int)blockIdx.x, (int)blockIdx.y, (int)blockIdx.z);
+}
+
 cudaError_t launch_apply_split(const ApplyParams& P, cudaStream_t s) {
   if (P.csum0) {
     const int C = P.C0 + P.C1;
@@ -290,16 +296,28 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// Bounded: a pipeline bug must surface as a launch failure (trap), never as a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
-  uint32_t ok;
+  uint32_t ok, spins = 0;
+  long long t0 = 0;
   do {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    if (!ok && (++spins & 0x3ffu) == 0) {
+      const long long t = clock64();
+      if (t0 == 0) t0 = t; else if (t - t0 > (1ll << 32)) __trap();     // ~2 s
+    }
   } while (!ok);
+}
+__device__ __forceinline__ void mbar_inval(uint64_t* bar) {
+  asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -539,6 +557,165 @@ __device__ __forceinline__ void tc_csum_chunk32(float (&v)[32], bool live, int l
   }
 }
 
+// The tap-GEMM epilogue (warps 2-5 of the CTA): TMEM -> registers -> (+bias, +residual, GroupNorm sums | qkv operand
+// split | split-K partial) -> HBM.  Shared by the one-tile-per-CTA kernel (PDL = true: it owns the grid-dependency
+// wait / trigger) and the persistent chain kernel (PDL = false: several tiles per CTA, s_bias is reused).
+template <int BN, int EPI, bool PDL>
+__device__ __forceinline__ void tc_epilogue(const TcConvParams& P, const Geo& g, const TcTile& T, int n0, int zidx,
+                                            uint32_t tmem_base, float* s_bias, uint64_t* bar_acc, uint32_t acc_parity,
+                                            long long* stamp) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = warp & 3;                       // TMEM lane quarter this warp may read
+  const int row = q * 32 + lane;                // row of the tile
+  int b, tok; tc_row_map(T, row, b, tok);
+  const bool live = b < P.B;
+  const size_t m = (size_t)b * g.L + tok;
+  if (PDL) MTV_PDL_WAIT();                        // residual / statistics buffers belong to earlier kernels
+  // Bias: small, touched once per step and evicted from L2 by the weight stream in between, i.e. a DRAM
+  // miss (~2000 cycles) if loaded on demand per chunk — so it is staged in smem during the main loop.
+  {
+    const int te = threadIdx.x - 64;
+    if (!PDL) asm volatile("bar.sync 1, 128;" ::: "memory");   // persistent caller: the previous tile's readers of s_bias are done
+    if (te < BN) s_bias[te] = P.bias ? __ldg(P.bias + n0 + te) : 0.0f;
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+  }
+  // the residual of the first 32-column chunk is fetched while the MMAs still run
+  const bool pre_res = EPI == 1 && live && P.resid;
+  float rpre[32];
+  if (pre_res) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) ld_global_nc_v8(P.resid + m * P.Cout + n0 + 8 * j, rpre + 8 * j);
+  }
+  mbar_wait(bar_acc, acc_parity);
+  if (PDL) MTV_PDL_TRIGGER();
+  if (stamp && threadIdx.x == 64) stamp[5] = clock64();            // accumulator complete
+  tc_fence_after();
+  int p = 0, y = 0, x = 0;
+  if (EPI == 3 || ((EPI == 1) && P.csum)) tc_decode_fast(T, tok, p, y, x);
+  const int pl_stat = p;
+#pragma unroll 1
+  for (int c0 = 0; c0 < BN; c0 += 32) {
+    uint32_t r[32];
+    __syncwarp();
+    {
+      uint32_t r2[32];
+      tmem_ld32_nowait(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+      tmem_ld32_nowait(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(BN + c0), r2);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+    }
+    const int n = n0 + c0;
+    // the chunk's bias is fetched in one go: loads inside the store loop would serialise behind the
+    // (possibly aliasing) stores and cost ~500 cycles each
+    float4 bpre[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) bpre[j] = *reinterpret_cast<const float4*>(&s_bias[c0 + 4 * j]);
+    float rnext[32];
+    const bool have_next = pre_res && (c0 + 32 < BN);
+    if (have_next) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) ld_global_nc_v8(P.resid + m * P.Cout + n + 32 + 8 * j, rnext + 8 * j);
+    }
+    if (!live) {
+      // rows of samples beyond the batch (partial last tile of a small level): nothing to store
+    } else if constexpr (EPI == 0) {
+      float* dst = P.partial + ((size_t)zidx * ((size_t)P.B * g.L) + m) * P.Cout + n;
+      float pv[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) pv[j] = __uint_as_float(r[j]);
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) st_global_v8(dst + j, pv + j);
+    } else {
+      float* dst = P.out + m * P.Cout + n;
+      float fv[32];
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+        {
+          const float4 bv = bpre[j >> 2];
+          v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+        }
+        if constexpr (EPI == 1) {
+          if (P.resid) { v.x += rpre[j]; v.y += rpre[j + 1]; v.z += rpre[j + 2]; v.w += rpre[j + 3]; }
+        }
+        if constexpr (EPI == 3) {
+          if (P.resid_mode == RS_UP2) {
+            const Geo gs = geo_down(g);
+            const int ts = tc_plane_off(gs, p) + (y >> 1) * gs.res + (x >> 1);
+            const float4 rv = __ldg(reinterpret_cast<const float4*>(P.resid + ((size_t)b * gs.L + ts) * P.Cout + n + j));
+            v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
+          } else {
+            const Geo gs = geo_up(g);
+            const int t0 = tc_plane_off(gs, p) + (2 * y) * gs.res + 2 * x;
+            const float* rp = P.resid + ((size_t)b * gs.L + t0) * P.Cout + n + j;
+            const float4 r0 = __ldg(reinterpret_cast<const float4*>(rp));
+            const float4 r1 = __ldg(reinterpret_cast<const float4*>(rp + P.Cout));
+            const float4 r2 = __ldg(reinterpret_cast<const float4*>(rp + (size_t)gs.res * P.Cout));
+            const float4 r3 = __ldg(reinterpret_cast<const float4*>(rp + (size_t)(gs.res + 1) * P.Cout));
+            v.x += 0.25f * (r0.x + r1.x + r2.x + r3.x); v.y += 0.25f * (r0.y + r1.y + r2.y + r3.y);
+            v.z += 0.25f * (r0.z + r1.z + r2.z + r3.z); v.w += 0.25f * (r0.w + r1.w + r2.w + r3.w);
+          }
+        }
+        fv[j] = v.x; fv[j + 1] = v.y; fv[j + 2] = v.z; fv[j + 3] = v.w;
+      }
+      if constexpr (EPI != 2) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) st_global_v8(dst + j, fv + j);
+      }
+      if constexpr (EPI == 2) {
+        // channels are head-major [h: q(D) k(D) v(D)] (unet.py:321); D >= 16, so every aligned run of 16
+        // channels is one of q / k / v of one head
+        const int Dh = P.Cout / (3 * P.qkv_heads);
+        const float qs = 1.4426950408889634f * rsqrtf((float)Dh);
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          const int nn = n + hf * 16;
+          const int hd = nn / (3 * Dh), rr = nn - hd * 3 * Dh;
+          const int kind = rr / Dh, d0 = rr - kind * Dh;
+          const size_t bh = (size_t)b * P.qkv_heads + hd;
+          __align__(16) __nv_bfloat16 hh[16], ll[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float val = kind == 0 ? fv[hf * 16 + i] * qs : fv[hf * 16 + i];
+            hh[i] = __float2bfloat16_rn(val);
+            ll[i] = __float2bfloat16_rn(val - __bfloat162float(hh[i]));
+          }
+          if (kind < 2) {
+            __nv_bfloat16* ph = reinterpret_cast<__nv_bfloat16*>(kind == 0 ? P.q_hi : P.k_hi) + (bh * g.L + tok) * Dh + d0;
+            __nv_bfloat16* pw = reinterpret_cast<__nv_bfloat16*>(kind == 0 ? P.q_lo : P.k_lo) + (bh * g.L + tok) * Dh + d0;
+            reinterpret_cast<uint4*>(ph)[0] = reinterpret_cast<const uint4*>(hh)[0];
+            reinterpret_cast<uint4*>(ph)[1] = reinterpret_cast<const uint4*>(hh)[1];
+            reinterpret_cast<uint4*>(pw)[0] = reinterpret_cast<const uint4*>(ll)[0];
+            reinterpret_cast<uint4*>(pw)[1] = reinterpret_cast<const uint4*>(ll)[1];
+          } else {
+            __nv_bfloat16* ph = reinterpret_cast<__nv_bfloat16*>(P.vt_hi) + (bh * Dh + d0) * g.L + tok;
+            __nv_bfloat16* pw = reinterpret_cast<__nv_bfloat16*>(P.vt_lo) + (bh * Dh + d0) * g.L + tok;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { ph[(size_t)i * g.L] = hh[i]; pw[(size_t)i * g.L] = ll[i]; }
+          }
+        }
+      }
+      if ((EPI == 1 || EPI == 3) && P.csum) {   // uniform: statistics of the tensor just written, for the next GroupNorm
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(fv[j]);
+      }
+    }
+    if ((EPI == 1 || EPI == 3) && P.csum) {
+      float fv[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) fv[j] = __uint_as_float(r[j]);
+      __syncwarp();
+      if (!T.small || T.spt == 1) tc_csum_chunk32(fv, live, lane, P.csum + (((size_t)(live ? b : 0) * 3 + pl_stat) * P.Cout + n) * 2);
+      else                        tc_csum_chunk(fv, live, lane, P.csum + (((size_t)(live ? b : 0) * 3 + pl_stat) * P.Cout + n) * 2);
+    }
+    if (have_next) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) rpre[j] = rnext[j];
+    }
+  }
+}
+
 // EPI selects the epilogue at compile time (the row-per-lane epilogue is instruction-issue bound, so the
 // paths a launch cannot take must not even be predicated off):
 //   0 split-K partial tile, 1 bias [+ same-geometry residual] [+ GroupNorm sums], 2 qkv operand split,
@@ -673,155 +850,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
     mbar_wait(&bar_acc, 0);
     MTV_PDL_TRIGGER();
   } else {
-    // =============================== epilogue ===================================
-    const int q = warp & 3;                       // TMEM lane quarter this warp may read
-    const int row = q * 32 + lane;                // row of the tile
-    int b, tok; tc_row_map(T, row, b, tok);
-    const bool live = b < P.B;
-    const size_t m = (size_t)b * g.L + tok;
-    MTV_PDL_WAIT();                                 // residual / statistics buffers belong to earlier kernels
-    // Bias: small, touched once per step and evicted from L2 by the weight stream in between, i.e. a DRAM
-    // miss (~2000 cycles) if loaded on demand per chunk — so it is staged in smem during the main loop.
-    {
-      const int te = threadIdx.x - 64;
-      if (te < BN) s_bias[te] = P.bias ? __ldg(P.bias + n0 + te) : 0.0f;
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-    }
-    // the residual of the first 32-column chunk is fetched while the MMAs still run
-    const bool pre_res = EPI == 1 && live && P.resid;
-    float rpre[32];
-    if (pre_res) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) ld_global_nc_v8(P.resid + m * P.Cout + n0 + 8 * j, rpre + 8 * j);
-    }
-    mbar_wait(&bar_acc, 0);
-    MTV_PDL_TRIGGER();
-    if (dbg && threadIdx.x == 64) s_stamp[5] = clock64();            // accumulator complete
-    tc_fence_after();
-    int p = 0, y = 0, x = 0;
-    if (EPI == 3 || ((EPI == 1) && P.csum)) tc_decode_fast(T, tok, p, y, x);
-    const int pl_stat = p;
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t r[32];
-      __syncwarp();
-      {
-        uint32_t r2[32];
-        tmem_ld32_nowait(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-        tmem_ld32_nowait(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(BN + c0), r2);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-        for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
-      }
-      const int n = n0 + c0;
-      // the chunk's bias is fetched in one go: loads inside the store loop would serialise behind the
-      // (possibly aliasing) stores and cost ~500 cycles each
-      float4 bpre[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) bpre[j] = *reinterpret_cast<const float4*>(&s_bias[c0 + 4 * j]);
-      float rnext[32];
-      const bool have_next = pre_res && (c0 + 32 < BN);
-      if (have_next) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) ld_global_nc_v8(P.resid + m * P.Cout + n + 32 + 8 * j, rnext + 8 * j);
-      }
-      if (!live) {
-        // rows of samples beyond the batch (partial last tile of a small level): nothing to store
-      } else if constexpr (EPI == 0) {
-        float* dst = P.partial + ((size_t)blockIdx.z * ((size_t)P.B * g.L) + m) * P.Cout + n;
-        float pv[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) pv[j] = __uint_as_float(r[j]);
-#pragma unroll
-        for (int j = 0; j < 32; j += 8) st_global_v8(dst + j, pv + j);
-      } else {
-        float* dst = P.out + m * P.Cout + n;
-        float fv[32];
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
-          {
-            const float4 bv = bpre[j >> 2];
-            v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
-          }
-          if constexpr (EPI == 1) {
-            if (P.resid) { v.x += rpre[j]; v.y += rpre[j + 1]; v.z += rpre[j + 2]; v.w += rpre[j + 3]; }
-          }
-          if constexpr (EPI == 3) {
-            if (P.resid_mode == RS_UP2) {
-              const Geo gs = geo_down(g);
-              const int ts = tc_plane_off(gs, p) + (y >> 1) * gs.res + (x >> 1);
-              const float4 rv = __ldg(reinterpret_cast<const float4*>(P.resid + ((size_t)b * gs.L + ts) * P.Cout + n + j));
-              v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
-            } else {
-              const Geo gs = geo_up(g);
-              const int t0 = tc_plane_off(gs, p) + (2 * y) * gs.res + 2 * x;
-              const float* rp = P.resid + ((size_t)b * gs.L + t0) * P.Cout + n + j;
-              const float4 r0 = __ldg(reinterpret_cast<const float4*>(rp));
-              const float4 r1 = __ldg(reinterpret_cast<const float4*>(rp + P.Cout));
-              const float4 r2 = __ldg(reinterpret_cast<const float4*>(rp + (size_t)gs.res * P.Cout));
-              const float4 r3 = __ldg(reinterpret_cast<const float4*>(rp + (size_t)(gs.res + 1) * P.Cout));
-              v.x += 0.25f * (r0.x + r1.x + r2.x + r3.x); v.y += 0.25f * (r0.y + r1.y + r2.y + r3.y);
-              v.z += 0.25f * (r0.z + r1.z + r2.z + r3.z); v.w += 0.25f * (r0.w + r1.w + r2.w + r3.w);
-            }
-          }
-          fv[j] = v.x; fv[j + 1] = v.y; fv[j + 2] = v.z; fv[j + 3] = v.w;
-        }
-        if constexpr (EPI != 2) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) st_global_v8(dst + j, fv + j);
-        }
-        if constexpr (EPI == 2) {
-          // channels are head-major [h: q(D) k(D) v(D)] (unet.py:321); D >= 16, so every aligned run of 16
-          // channels is one of q / k / v of one head
-          const int Dh = P.Cout / (3 * P.qkv_heads);
-          const float qs = 1.4426950408889634f * rsqrtf((float)Dh);
-#pragma unroll
-          for (int hf = 0; hf < 2; ++hf) {
-            const int nn = n + hf * 16;
-            const int hd = nn / (3 * Dh), rr = nn - hd * 3 * Dh;
-            const int kind = rr / Dh, d0 = rr - kind * Dh;
-            const size_t bh = (size_t)b * P.qkv_heads + hd;
-            __align__(16) __nv_bfloat16 hh[16], ll[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float val = kind == 0 ? fv[hf * 16 + i] * qs : fv[hf * 16 + i];
-              hh[i] = __float2bfloat16_rn(val);
-              ll[i] = __float2bfloat16_rn(val - __bfloat162float(hh[i]));
-            }
-            if (kind < 2) {
-              __nv_bfloat16* ph = reinterpret_cast<__nv_bfloat16*>(kind == 0 ? P.q_hi : P.k_hi) + (bh * g.L + tok) * Dh + d0;
-              __nv_bfloat16* pw = reinterpret_cast<__nv_bfloat16*>(kind == 0 ? P.q_lo : P.k_lo) + (bh * g.L + tok) * Dh + d0;
-              reinterpret_cast<uint4*>(ph)[0] = reinterpret_cast<const uint4*>(hh)[0];
-              reinterpret_cast<uint4*>(ph)[1] = reinterpret_cast<const uint4*>(hh)[1];
-              reinterpret_cast<uint4*>(pw)[0] = reinterpret_cast<const uint4*>(ll)[0];
-              reinterpret_cast<uint4*>(pw)[1] = reinterpret_cast<const uint4*>(ll)[1];
-            } else {
-              __nv_bfloat16* ph = reinterpret_cast<__nv_bfloat16*>(P.vt_hi) + (bh * Dh + d0) * g.L + tok;
-              __nv_bfloat16* pw = reinterpret_cast<__nv_bfloat16*>(P.vt_lo) + (bh * Dh + d0) * g.L + tok;
-#pragma unroll
-              for (int i = 0; i < 16; ++i) { ph[(size_t)i * g.L] = hh[i]; pw[(size_t)i * g.L] = ll[i]; }
-            }
-          }
-        }
-        if ((EPI == 1 || EPI == 3) && P.csum) {   // uniform: statistics of the tensor just written, for the next GroupNorm
-#pragma unroll
-          for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(fv[j]);
-        }
-      }
-      if ((EPI == 1 || EPI == 3) && P.csum) {
-        float fv[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) fv[j] = __uint_as_float(r[j]);
-        __syncwarp();
-        if (!T.small || T.spt == 1) tc_csum_chunk32(fv, live, lane, P.csum + (((size_t)(live ? b : 0) * 3 + pl_stat) * P.Cout + n) * 2);
-        else                        tc_csum_chunk(fv, live, lane, P.csum + (((size_t)(live ? b : 0) * 3 + pl_stat) * P.Cout + n) * 2);
-      }
-      if (have_next) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) rpre[j] = rnext[j];
-      }
-    }
+    tc_epilogue<BN, EPI, true>(P, g, T, n0, (int)blockIdx.z, tmem_base, s_bias, &bar_acc, 0u, dbg ? s_stamp : nullptr);
   }
   if (dbg && threadIdx.x == 64) s_stamp[6] = clock64();              // epilogue stores issued
   tc_fence_before();
@@ -847,14 +876,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
 // split-K epilogue for the tensor-core path (fixed summation order).  A CTA owns 32 rows x 32
 // channels: warp w = channel quad, lane = row, so the per-channel statistics reduce with three
 // shuffles over aligned 8-row groups (never straddling a (sample, plane) boundary).
-__global__ void __launch_bounds__(256) k_tc_splitk_epilogue(const __grid_constant__ TcConvParams P) {
-  MTV_PDL_TRIGGER();
-  MTV_PDL_WAIT();
+__device__ __forceinline__ void tc_splitk_unit(const TcConvParams& P, int mblk, int nblk) {
   const Geo g = P.geo;
   const size_t M = (size_t)P.B * g.L;
   const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
-  const size_t m = (size_t)blockIdx.x * 32 + lane;
-  const int n = blockIdx.y * 32 + wq * 4;
+  const size_t m = (size_t)mblk * 32 + lane;
+  const int n = nblk * 32 + wq * 4;
   float4 bv0 = make_float4(0.f, 0.f, 0.f, 0.f);
   if (P.bias) bv0 = __ldg(reinterpret_cast<const float4*>(P.bias + n));     // cold line: issue first
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -910,6 +937,337 @@ __global__ void __launch_bounds__(256) k_tc_splitk_epilogue(const __grid_constan
       for (int i = 0; i < 4; ++i) { atomicAdd(dst + 2 * i, (double)v[i]); atomicAdd(dst + 2 * i + 1, (double)q[i]); }
     }
   }
+}
+__global__ void __launch_bounds__(256) k_tc_splitk_epilogue(const __grid_constant__ TcConvParams P) {
+  MTV_PDL_TRIGGER();
+  MTV_PDL_WAIT();
+  tc_splitk_unit(P, (int)blockIdx.x, (int)blockIdx.y);
+}
+
+// ------------------------------------------------------------------ persistent chain kernel
+// k_chain executes a run of {apply, tap-GEMM, split-K reduction} sub-ops that the launch plan would otherwise issue as
+// separate kernels.  Grid = min(#SMs, work units) CTAs of 256 threads, one per SM (208 KB of shared memory), all
+// co-resident, so a sense-free counting barrier in global memory can stand in for each kernel boundary:
+//   * the operand ring, mbarriers and the 256-column TMEM allocation are set up once per chain, not once per op;
+//   * every sub-op is a persistent loop `unit = blockIdx.x; unit < units; unit += gridDim.x`;
+//   * weights do not depend on earlier sub-ops: the W halves of the next GEMM's first stages are requested BEFORE the
+//     barrier, so their HBM latency overlaps the barrier and the sub-ops in between.
+// GEMM roles: warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-5 = epilogue (tc_epilogue), warps 6-7 idle.
+constexpr int CH_THREADS = 256;
+constexpr int CH_PIPE_BYTES = 4 * tc_stage_bytes(64);
+static_assert(tc_stages(64) * tc_stage_bytes(64) == CH_PIPE_BYTES && tc_stages(128) * tc_stage_bytes(128) == CH_PIPE_BYTES, "ring size");
+constexpr int CH_AFF_FLOATS = 4096;                      // a[C] | d[C] of the apply sub-op, C <= 2048
+constexpr int CH_SMEM_BYTES = 1024 + CH_PIPE_BYTES + CH_AFF_FLOATS * 4;
+constexpr int CH_TMEM_COLS = 256;
+
+struct ChainGemmGeo { int kch, it_main, it_total, ks, per, mt, nt, ntiles; };
+__host__ __device__ inline ChainGemmGeo chain_gemm_geo(const TcConvParams& P, int BN) {
+  ChainGemmGeo G;
+  G.kch = P.Cin / TC_BK; G.it_main = P.taps * G.kch; G.it_total = G.it_main + P.Cin2 / TC_BK;
+  G.ks = P.ksplit > 1 ? P.ksplit : 1; G.per = (G.it_total + G.ks - 1) / G.ks;
+  const int M = P.B * P.geo.L;
+  G.mt = P.geo.L > TC_BM ? M / TC_BM : (P.B + (TC_BM / P.geo.L) - 1) / (TC_BM / P.geo.L);
+  G.nt = P.Cout / BN; G.ntiles = G.mt * G.nt * G.ks;
+  return G;
+}
+__host__ __device__ inline int chain_apply_units(const ApplyParams& P) {
+  const int nxy = (P.geo.res * P.geo.res + P.chunk_tokens - 1) / P.chunk_tokens;
+  const int npl = (P.geo.t * P.geo.res + P.chunk_tokens - 1) / P.chunk_tokens;
+  return (nxy + 2 * npl) * P.B;
+}
+int chain_max_grid_units(const ChainOp& op) {
+  if (op.type == CH_APPLY) return chain_apply_units(op.apply);
+  if (op.type == CH_GEMM) return chain_gemm_geo(op.conv, op.conv.bn).ntiles;
+  return (op.conv.B * op.conv.geo.L / 32) * (op.conv.Cout / 32);
+}
+
+// W halves (hi | lo, adjacent: the stacked-N operand) of K-iteration `it` of the tile at output channel n0
+__device__ __forceinline__ void chain_load_W(const TcConvParams& PG, int BN, const ChainGemmGeo& G, int Cout, int it, int n0,
+                                             uint32_t sW_hi, uint32_t fb) {
+  const uint32_t sW_lo = sW_hi + (uint32_t)BN * 128u;
+  if (it >= G.it_main) {
+    const int c2 = (it - G.it_main) * TC_BK;
+    tma_load_2d(sW_hi, &PG.tmW2_hi, fb, c2, n0);
+    tma_load_2d(sW_lo, &PG.tmW2_lo, fb, c2, n0);
+  } else {
+    const int tap = it / G.kch, c0 = (it - tap * G.kch) * TC_BK;
+    tma_load_2d(sW_hi, &PG.tmW_hi, fb, c0, tap * Cout + n0);
+    tma_load_2d(sW_lo, &PG.tmW_lo, fb, c0, tap * Cout + n0);
+  }
+}
+
+// Thread 0, pipeline idle and barriers freshly initialised: request the W halves of the first stages of this CTA's first
+// tile of GEMM sub-op `PG` (global-memory descriptor).  Returns the number of stages requested.
+__device__ __forceinline__ int chain_prefetch_W(const TcConvParams& PG, uint32_t smem0, uint64_t* bar_full) {
+  const int BN = PG.bn;
+  const ChainGemmGeo G = chain_gemm_geo(PG, BN);
+  const int tile = blockIdx.x;
+  if (tile >= G.ntiles) return 0;
+  const int r = tile / G.mt, n0 = (r % G.nt) * BN, z = r / G.nt;
+  const int it0 = z * G.per, it1 = min(G.it_total, it0 + G.per);
+  const int NS = tc_stages(BN), STAGE = tc_stage_bytes(BN);
+  const int npre = min(NS, it1 - it0);
+  const int Cout = PG.Cout;
+  prefetch_tmap(&PG.tmA_hi[0]); prefetch_tmap(&PG.tmA_lo[0]);
+  for (int i = 0; i < npre; ++i) {
+    mbar_expect_tx(&bar_full[i], (uint32_t)STAGE);
+    chain_load_W(PG, BN, G, Cout, it0 + i, n0, smem0 + i * STAGE + 2 * TC_BM * 128, smem_u32(&bar_full[i]));
+  }
+  return npre;
+}
+
+// PG: the op in global memory (tensor maps); P: its scalar fields staged in shared memory.
+template <int BN>
+__device__ __noinline__ void chain_gemm(const TcConvParams& PG, const TcConvParams& P, uint32_t smem0, uint64_t* bar_full, uint64_t* bar_empty,
+                           uint64_t* bar_acc, uint64_t* bar_accfree, uint32_t tmem_base, float* s_bias, int npre) {
+  constexpr int NS = tc_stages(BN);
+  constexpr int STAGE = tc_stage_bytes(BN);
+  constexpr uint32_t IDESC = umma_idesc_bf16(TC_BM, BN);
+  constexpr uint32_t IDESC2 = umma_idesc_bf16(TC_BM, 2 * BN);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp >= 6) return;
+  const Geo g = P.geo;
+  const ChainGemmGeo G = chain_gemm_geo(P, BN);
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    if (lane == 0) {
+      const int taps = P.taps, Cout = P.Cout;
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < G.ntiles; tile += gridDim.x) {
+        const int mx = tile % G.mt, r = tile / G.mt, n0 = (r % G.nt) * BN, z = r / G.nt;
+        const TcTile T = tc_tile(g, mx);
+        const int it0 = z * G.per, it1 = min(G.it_total, it0 + G.per);
+        for (int it = it0; it < it1; ++it) {
+          const uint32_t sA_hi = smem0 + stage * STAGE, sA_lo = sA_hi + TC_BM * 128, sW_hi = sA_lo + TC_BM * 128;
+          const uint32_t fb = smem_u32(&bar_full[stage]);
+          if (npre > 0) {
+            --npre;                                   // W of this stage was requested before the grid barrier
+          } else {
+            mbar_wait(&bar_empty[stage], phase ^ 1u);
+            mbar_expect_tx(&bar_full[stage], (uint32_t)STAGE);
+            chain_load_W(PG, BN, G, Cout, it, n0, sW_hi, fb);
+          }
+          if (it >= G.it_main) {                      // second K-segment: 1x1 conv of the skip operand
+            tc_load_A(g, T, PG.tmA2_hi, PG.tmA2_lo, 1, 0, (it - G.it_main) * TC_BK, sA_hi, sA_lo, fb);
+          } else {
+            const int tap = it / G.kch, c0 = (it - tap * G.kch) * TC_BK;
+            tc_load_A(g, T, PG.tmA_hi, PG.tmA_lo, taps, tap, c0, sA_hi, sA_lo, fb);
+          }
+          if (++stage == NS) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer =================================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0, tl = 0;
+      for (int tile = blockIdx.x; tile < G.ntiles; tile += gridDim.x) {
+        const int z = (tile / G.mt) / G.nt;
+        const int it0 = z * G.per, it1 = min(G.it_total, it0 + G.per);
+        mbar_wait(bar_accfree, (tl & 1u) ^ 1u);       // the epilogue has read the previous tile out of TMEM
+        tc_fence_after();
+        for (int it = it0; it < it1; ++it) {
+          mbar_wait(&bar_full[stage], phase);
+          tc_fence_after();
+          const uint32_t sA_hi = smem0 + stage * STAGE, sA_lo = sA_hi + TC_BM * 128;
+          const uint32_t sW_hi = sA_lo + TC_BM * 128;
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k) {
+            const uint64_t a_hi = umma_desc_sw128(sA_hi + k * 32), a_lo = umma_desc_sw128(sA_lo + k * 32);
+            const uint64_t w_hi = umma_desc_sw128(sW_hi + k * 32);          // rows [0,BN) = W_hi, [BN,2BN) = W_lo
+            umma_bf16(tmem_base, a_hi, w_hi, IDESC2, (it > it0 || k > 0) ? 1u : 0u);
+            umma_bf16(tmem_base, a_lo, w_hi, IDESC, 1u);
+          }
+          umma_commit(&bar_empty[stage]);
+          if (++stage == NS) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(bar_acc);
+        ++tl;
+      }
+    }
+  } else {
+    // =============================== epilogue ===================================
+    const int epi = P.ksplit > 1 ? 0 : (P.qkv_heads ? 2 : ((P.resid && P.resid_mode != RS_NONE) ? 3 : 1));
+    uint32_t tl = 0;
+    for (int tile = blockIdx.x; tile < G.ntiles; tile += gridDim.x) {
+      const int mx = tile % G.mt, r = tile / G.mt, n0 = (r % G.nt) * BN, z = r / G.nt;
+      const TcTile T = tc_tile(g, mx);
+      switch (epi) {
+        case 0: tc_epilogue<BN, 0, false>(P, g, T, n0, z, tmem_base, s_bias, bar_acc, tl & 1u, nullptr); break;
+        case 1: tc_epilogue<BN, 1, false>(P, g, T, n0, z, tmem_base, s_bias, bar_acc, tl & 1u, nullptr); break;
+        case 2: tc_epilogue<BN, 2, false>(P, g, T, n0, z, tmem_base, s_bias, bar_acc, tl & 1u, nullptr); break;
+        default: tc_epilogue<BN, 3, false>(P, g, T, n0, z, tmem_base, s_bias, bar_acc, tl & 1u, nullptr); break;
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_accfree);
+      ++tl;
+    }
+  }
+}
+
+__device__ __noinline__ void chain_apply(const ApplyParams& P, float* s_aff, double* s_mean, double* s_rstd) {
+  mtv_prefetch_slice(P.pf0, P.pf1, P.pf_bytes, blockIdx.x, gridDim.x);
+  const Geo g = P.geo;
+  const int nxy = (g.res * g.res + P.chunk_tokens - 1) / P.chunk_tokens, npl = (g.t * g.res + P.chunk_tokens - 1) / P.chunk_tokens;
+  const int per_b = nxy + 2 * npl, units = per_b * P.B;
+  bool first = true;
+  for (int u = blockIdx.x; u < units; u += gridDim.x) {
+    if (!first) __syncthreads();                     // the previous unit's readers of the affine table are done
+    first = false;
+    const int b = u / per_b;
+    int r = u - b * per_b, p = 0;
+    if (r >= nxy) { r -= nxy; p = 1; if (r >= npl) { r -= npl; p = 2; } }
+    apply_norm_unit(P, s_aff, s_mean, s_rstd, r, p, b);
+  }
+}
+
+__device__ __noinline__ void chain_reduce(const TcConvParams& P) {
+  const int mb = (P.B * P.geo.L) / 32, nb = P.Cout / 32;
+  for (int u = blockIdx.x; u < mb * nb; u += gridDim.x) tc_splitk_unit(P, u % mb, u / mb);
+}
+
+// Thread 0 of every CTA, between two __syncthreads: all `gridDim.x` CTAs are co-resident (host guarantees grid <= #SMs at one
+// CTA per SM), so spinning is safe; bounded anyway (trap, not hang).
+__device__ __forceinline__ void chain_grid_barrier(unsigned int* ctr, unsigned int target) {
+  __threadfence();
+  atomicAdd(ctr, 1u);
+  unsigned int v, spins = 0;
+  long long t0 = 0;
+  for (;;) {
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+    if (v >= target) break;
+    if ((++spins & 0xffu) == 0) {
+      const long long t = clock64();
+      if (t0 == 0) t0 = t; else if (t - t0 > (1ll << 32)) __trap();
+    }
+  }
+  __threadfence();
+}
+
+template <typename S>
+__device__ __forceinline__ void chain_copy_words(S* dst, const S* src, size_t from_byte) {
+  const uint32_t* s = reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(src) + from_byte);
+  uint32_t* d = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(dst) + from_byte);
+  const int n = (int)((sizeof(S) - from_byte) / 4);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) d[i] = __ldg(s + i);
+}
+
+__global__ void __launch_bounds__(CH_THREADS, 1) k_chain(const ChainOp* __restrict__ ops, int nops, unsigned int* counters) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_full[4], bar_empty[4], bar_acc, bar_accfree;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ __align__(16) float s_bias[128];
+  __shared__ double s_mean[32], s_rstd[32];
+  __shared__ TcConvParams s_cp;                    // scalar fields only (the tensor maps are used from global memory)
+  __shared__ ApplyParams s_ap;
+  static_assert(sizeof(TcConvParams) % 4 == 0 && sizeof(ApplyParams) % 4 == 0 && offsetof(TcConvParams, Cin2) % 4 == 0, "word copies");
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  float* s_aff = reinterpret_cast<float*>(smem_raw + (smem0 - smem_u32(smem_raw)) + CH_PIPE_BYTES);
+  const bool dbg = g_tc_dbg != nullptr;
+
+  auto init_bars = [&]() {
+    for (int s = 0; s < 4; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
+    mbar_init(&bar_acc, 1); mbar_init(&bar_accfree, 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  };
+  auto next_gemm_prefetch = [&](int from) -> int {
+    for (int j = from; j < nops; ++j)
+      if (ops[j].type == CH_GEMM) return chain_prefetch_W(ops[j].conv, smem0, bar_full);
+    return 0;
+  };
+  if (tid == 0) init_bars();
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"((uint32_t)CH_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  int npre = 0;                                    // thread 0: stages of the next GEMM whose W halves are already in flight
+  if (tid == 0) npre = next_gemm_prefetch(0);      // weights never depend on the previous kernel
+  MTV_PDL_WAIT();
+
+  for (int i = 0; i < nops; ++i) {
+    const ChainOp& op = ops[i];
+    const int type = op.type;
+    long long t_start = 0;
+    if (dbg && tid == 0) t_start = gtime_ns();
+    if (i == nops - 1) MTV_PDL_TRIGGER();          // only this CTA's last sub-op remains
+    if (type == CH_APPLY) chain_copy_words(&s_ap, &op.apply, 0);
+    else                  chain_copy_words(&s_cp, &op.conv, offsetof(TcConvParams, Cin2));
+    __syncthreads();
+    if (type == CH_APPLY) {
+      chain_apply(s_ap, s_aff, s_mean, s_rstd);
+    } else if (type == CH_GEMM) {
+      if (s_cp.bn == 64) chain_gemm<64>(op.conv, s_cp, smem0, bar_full, bar_empty, &bar_acc, &bar_accfree, tmem_base, s_bias, npre);
+      else               chain_gemm<128>(op.conv, s_cp, smem0, bar_full, bar_empty, &bar_acc, &bar_accfree, tmem_base, s_bias, npre);
+      npre = 0;
+    } else {
+      chain_reduce(s_cp);
+    }
+    if (i == nops - 1) {
+      if (dbg && tid == 0) {
+        const unsigned int slot = atomicAdd(&g_tc_dbg_count, 1u);
+        if (slot < g_tc_dbg_cap) {
+          long long* rec = g_tc_dbg + (size_t)slot * 16;
+          rec[0] = (1ll << 62) | ((long long)type << 48) | ((long long)i << 32) | (long long)blockIdx.x;
+          rec[1] = t_start; rec[2] = gtime_ns(); rec[3] = rec[2]; rec[4] = (long long)ops; rec[5] = nops;
+        }
+      }
+      break;
+    }
+    asm volatile("fence.proxy.async;" ::: "memory");   // this thread's global stores vs. later TMA (async-proxy) reads by other CTAs
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      long long t_work = 0;
+      if (dbg) t_work = gtime_ns();
+      if (type == CH_GEMM) {                       // pipeline drained: fresh barriers for the next GEMM, its first W requests go out now
+        tc_fence_after();
+        for (int s = 0; s < 4; ++s) { mbar_inval(&bar_full[s]); mbar_inval(&bar_empty[s]); }
+        mbar_inval(&bar_acc); mbar_inval(&bar_accfree);
+        init_bars();
+        npre = next_gemm_prefetch(i + 1);
+      }
+      chain_grid_barrier(counters, (unsigned int)(i + 1) * gridDim.x);
+      asm volatile("fence.proxy.async;" ::: "memory");
+      if (dbg) {
+        const unsigned int slot = atomicAdd(&g_tc_dbg_count, 1u);
+        if (slot < g_tc_dbg_cap) {
+          long long* rec = g_tc_dbg + (size_t)slot * 16;
+          rec[0] = (1ll << 62) | ((long long)type << 48) | ((long long)i << 32) | (long long)blockIdx.x;
+          rec[1] = t_start; rec[2] = t_work; rec[3] = gtime_ns(); rec[4] = (long long)ops; rec[5] = nops;
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)CH_TMEM_COLS) : "memory");
+  }
+  if (tid == 0 && nops > 1) {                      // the last CTA out re-arms the barrier for the next launch of this chain
+    __threadfence();
+    const unsigned int prev = atomicAdd(counters + 1, 1u);
+    if (prev == gridDim.x - 1) { atomicExch(counters, 0u); atomicExch(counters + 1, 0u); }
+  }
+}
+
+cudaError_t launch_chain(const ChainLaunch& L, cudaStream_t s) {
+  if (L.nops < 1 || L.grid < 1) return cudaErrorInvalidValue;
+  cudaError_t e = cudaFuncSetAttribute(k_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM_BYTES);
+  if (e != cudaSuccess) return e;
+  e = launch_kc(PDL_CLASS_CONV_TC, k_chain, dim3(L.grid), dim3(CH_THREADS), (size_t)CH_SMEM_BYTES, s, L.ops, L.nops, L.counters);
+  if (e != cudaSuccess) return e;
+  return cudaGetLastError();
 }
 
 cudaError_t launch_conv_tc(const TcConvParams& P, cudaStream_t s) {

@@ -130,6 +130,9 @@ struct Op {
   std::string name; int phase = 1;      // 0 = before graph (reads caller pointers), 1 = graph body, 2 = after
   int launches = 1; double flops = 0, bytes = 0;
   std::function<cudaError_t(cudaStream_t)> fn;
+  // ops the persistent chain kernel can absorb keep their parameter block (see fuse_chains)
+  int ctype = -1;                       // -1: not chainable, CH_APPLY, CH_GEMM (+ its split-K reduction)
+  std::shared_ptr<ApplyParams> ap; std::shared_ptr<TcConvParams> tc;
 };
 
 struct Plan {
@@ -160,7 +163,7 @@ struct MtvHandle_t {
   std::map<int, std::unique_ptr<Plan>> plans;
   Plan* last_plan = nullptr;
   int64_t weight_bytes = 0;
-  int tc_mask = 0xfff;
+  int tc_mask = 0xfff;      // bit 12 (persistent chain kernel) is opt-in: measured slower, profiles/r01_s2_chain_experiment.md
   cudaStream_t cap_stream = nullptr;
   cudaStream_t capture_stream() {
     if (!cap_stream) CK(cudaStreamCreateWithFlags(&cap_stream, cudaStreamNonBlocking));
@@ -461,6 +464,7 @@ struct Builder {
     }
     Op op; op.name = "apply:" + name; op.bytes = (double)B * g.L * C * (raw_out ? 12 : 8);
     op.fn = [A](cudaStream_t s) { return launch_apply_split(A, s); };
+    if (A.csum0 && C <= 2048) { op.ctype = CH_APPLY; op.ap = std::make_shared<ApplyParams>(A); }
     pl->ops.push_back(op);
     return out;
   }
@@ -551,7 +555,55 @@ struct Builder {
     op.flops = 2.0 * M * P.Cout * Ktot;
     op.bytes = 4.0 * Ktot * P.Cout + 4.0 * M * Ktot / S.taps + 4.0 * M * P.Cout;
     op.fn = [T](cudaStream_t s) { return launch_conv_tc(T, s); };
+    op.ctype = CH_GEMM; op.tc = std::make_shared<TcConvParams>(T);
     pl->ops.push_back(op);
+  }
+
+  // Runs of consecutive chainable graph-body ops become ONE launch of the persistent chain kernel (kernels_tc.cu:
+  // k_chain): kernel boundaries turn into grid-wide barriers, per-kernel prologues are paid once per chain.
+  bool use_chains() const { return h->cfg.kernel_path != 1 && ((h->tc_mask >> 12) & 1); }
+  void fuse_chains() {
+    if (!use_chains()) return;
+    std::vector<Op> out;
+    const int G = h->num_sms;
+    size_t i = 0;
+    while (i < pl->ops.size()) {
+      size_t j = i;
+      while (j < pl->ops.size() && pl->ops[j].phase == 1 && pl->ops[j].ctype >= 0) ++j;
+      std::vector<ChainOp> sub;
+      for (size_t k = i; k < j; ++k) {
+        const Op& o = pl->ops[k];
+        ChainOp c; memset(&c, 0, sizeof(c));
+        if (o.ctype == CH_APPLY) {
+          c.type = CH_APPLY; c.apply = *o.ap;
+          // one wave of units: the smallest power-of-two chunk whose unit count fits the grid
+          int chunk = 1;
+          for (;; chunk <<= 1) { c.apply.chunk_tokens = chunk; if (chain_max_grid_units(c) <= G || chunk >= 4096) break; }
+          sub.push_back(c);
+        } else {
+          c.type = CH_GEMM; c.conv = *o.tc; sub.push_back(c);
+          if (o.tc->ksplit > 1) { c.type = CH_REDUCE; sub.push_back(c); }
+        }
+      }
+      if (sub.size() < 2) {                         // nothing to fuse: keep the stand-alone launch(es)
+        for (size_t k = i; k < std::max(j, i + 1); ++k) out.push_back(pl->ops[k]);
+        i = std::max(j, i + 1);
+        continue;
+      }
+      int grid = 1;
+      for (const ChainOp& c : sub) grid = std::max(grid, std::min(G, chain_max_grid_units(c)));
+      ChainLaunch L{};
+      ChainOp* dops = (ChainOp*)dalloc(sub.size() * sizeof(ChainOp));
+      CK(cudaMemcpy(dops, sub.data(), sub.size() * sizeof(ChainOp), cudaMemcpyHostToDevice));
+      L.ops = dops; L.nops = (int)sub.size(); L.counters = (unsigned int*)dalloc(256, true); L.grid = grid;
+      Op op; op.name = "chain:" + pl->ops[i].name.substr(pl->ops[i].name.find(':') + 1) + "+" + std::to_string(sub.size());
+      op.launches = 1;
+      for (size_t k = i; k < j; ++k) { op.flops += pl->ops[k].flops; op.bytes += pl->ops[k].bytes; }
+      op.fn = [L](cudaStream_t s) { return launch_chain(L, s); };
+      out.push_back(op);
+      i = j;
+    }
+    pl->ops.swap(out);
   }
 
   bool fuse_launches() const { return h->cfg.kernel_path != 1 && ((h->tc_mask >> 9) & 1); }
@@ -858,6 +910,7 @@ Plan* get_plan(MtvHandle_t* h, int B) {
   pl->B = B;
   Builder b(h, pl.get());
   b.build();
+  b.fuse_chains();
   CK(cudaDeviceSynchronize());   // memsets of the statistics scratch
   Plan* raw = pl.get();
   h->plans[B] = std::move(pl);

@@ -78,6 +78,19 @@ struct AttnTcParams {
 cudaError_t launch_qkv_split(const QkvSplitParams& P, cudaStream_t s);
 cudaError_t launch_attn_tc(const AttnTcParams& P, cudaStream_t s);
 
+// Persistent chain kernel: a run of consecutive {apply, tap-GEMM, split-K reduction} launches executed by ONE
+// cooperative-style grid (<= one CTA per SM, all co-resident) with a grid-wide barrier between sub-ops instead of a
+// kernel boundary.  At small batch the forward is bound by launch gaps and per-kernel prologues, not by work.
+enum { CH_APPLY = 0, CH_GEMM = 1, CH_REDUCE = 2 };
+struct ChainOp {               // device-resident array element (tensor maps live in global memory)
+  int type; int pad_[15];
+  TcConvParams conv;           // CH_GEMM, CH_REDUCE
+  ApplyParams apply;           // CH_APPLY (fused-GroupNorm mode only)
+};
+struct ChainLaunch { const ChainOp* ops; int nops; unsigned int* counters /* [2], zero, self-resetting */; int grid; };
+cudaError_t launch_chain(const ChainLaunch& L, cudaStream_t s);
+int         chain_max_grid_units(const ChainOp& op);   // work units of one sub-op (host-side, for sizing the grid)
+
 cudaError_t launch_apply_split(const ApplyParams& P, cudaStream_t s);
 cudaError_t launch_repack_split_w(const float* src, void* hi, void* lo, int Cout, int Cin, int taps, cudaStream_t s);
 cudaError_t launch_conv_tc(const TcConvParams& P, cudaStream_t s);

@@ -38,6 +38,7 @@ torch.cuda.synchronize()
 _lib.check(lib.mtv_debug_tc_timing(h, None, 0, ctypes.byref(cnt)), "disarm")
 n = min(cnt.value, cap)
 rec = buf.cpu().view(cap, 16)[:n]
+rec = rec[(rec[:, 0] >> 62) == 0]          # chain-kernel records (scripts/chain_timing.py) carry bit 62
 print(f"{n} CTA records in one forward (B={B})")
 groups = defaultdict(list)
 for r in rec.tolist():

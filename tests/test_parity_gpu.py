@@ -152,14 +152,16 @@ def test_eager_capture_replay_are_bit_identical():
 
 
 def test_launch_modes_do_not_change_results(monkeypatch):
-    """Programmatic dependent launch (any class mask) and the launch fusions only reorder / overlap work:
-    outputs must be bit-identical to the plain serial plan."""
+    """Programmatic dependent launch (any class mask), the launch fusions and the persistent chain kernel (kernel
+    boundaries replaced by grid barriers) only reorder / overlap work: outputs must be bit-identical to the plain
+    serial plan."""
     cfg = config_by_name("tiny")
     x, cond, ic, t = synth_inputs(2, seed=88, t=[5, 900])
     outs = {}
     for name, env in (("pdl default", {}), ("pdl off", {"MTV_PDL": "0"}), ("pdl all", {"MTV_PDL": "31"}),
-                      ("no graph", {"MTV_NO_GRAPH": "1"})):
-        for k in ("MTV_PDL", "MTV_NO_GRAPH"):
+                      ("no graph", {"MTV_NO_GRAPH": "1"}),
+                      ("chain kernel", {"MTV_TC_MASK": "0x1fff"}), ("chain kernel, pdl off", {"MTV_TC_MASK": "0x1fff", "MTV_PDL": "0"})):
+        for k in ("MTV_PDL", "MTV_NO_GRAPH", "MTV_TC_MASK"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
