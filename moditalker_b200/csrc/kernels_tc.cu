@@ -28,7 +28,8 @@
 namespace mtv {
 
 // ------------------------------------------------------------------ apply + split
-__device__ __forceinline__ float silu_tc(float v) { return v / (1.0f + __expf(-v)); }
+// x * sigmoid(x) with a fast (2-ulp) division: the IEEE division's slow-path call bloats the unrolled producers
+__device__ __forceinline__ float silu_tc(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
 
 __device__ __forceinline__ void tc_decode_tok(const Geo& g, int tok, int& p, int& y, int& x) {
   const int nxy = g.res * g.res;
@@ -422,6 +423,9 @@ constexpr int TC_BM = 128, TC_BK = 64, TC_THREADS = 192;
 __host__ __device__ constexpr int tc_stage_bytes(int BN) { return 2 * TC_BM * 128 + 2 * BN * 128; }
 __host__ __device__ constexpr int tc_stages(int BN) { return BN == 64 ? 4 : 3; }
 __host__ __device__ constexpr int tc_smem_bytes(int BN) { return tc_stages(BN) * tc_stage_bytes(BN) + 1024; }
+// direct mode: 8 producer warps (two groups alternating K-iterations) + the affine table behind the operand ring
+constexpr int TC_THREADS_DIRECT = 320;
+__host__ __device__ constexpr int tc_smem_bytes_direct(int BN) { return tc_smem_bytes(BN) + TC_TABLE_ENTRIES * 8; }
 
 // Tile geometry.  Levels with >= 128 tokens per sample (L = 2048, 512): a tile is 128
 // consecutive tokens of one plane of one sample.  Small levels (L = 128, 32): a tile is
@@ -554,6 +558,233 @@ __device__ __forceinline__ void tc_csum_chunk32(float (&v)[32], bool live, int l
   if (__any_sync(0xffffffffu, live)) {
     atomicAdd(csum_bp + 2 * lane, (double)v[0]);
     atomicAdd(csum_bp + 2 * lane + 1, (double)q[0]);
+  }
+}
+
+// ------------------------------------------------------------------ direct A operand (no apply pass)
+// sample-plane slot of a tile row in the affine table
+__device__ __forceinline__ int tc_sp_index(const TcTile& T, bool per_plane, int b, int p) {
+  return T.small ? (per_plane ? (b - T.b0) * 3 + p : (b - T.b0)) : 0;
+}
+
+// Affine table of one K-segment for this CTA's tile: tbl[sp][c] = (a, d) with y = x*a + d the GroupNorm (+FiLM) of channel c
+// for the (sample, plane) pair sp.  Same arithmetic (fp64 statistics, fp32 result) as apply_norm_unit.  `scratch` holds
+// 2 doubles per (sp, group).  Called by all `nthreads` threads of the CTA (nthreads % 32 == 0).
+__device__ __forceinline__ void tc_build_table(const DirectSeg& S, const Geo& g, const TcTile& T, int B, float2* tbl, double* scratch,
+                                               int nthreads) {
+  const int C = S.C0 + S.C1, cpg = C / 32;
+  const Geo gs = S.resample == RS_NONE ? g : (S.resample == RS_UP2 ? geo_down(g) : geo_up(g));
+  const bool per_plane = S.mode == DS_NORM_CSUM ? !S.joint : S.nrm_nseg == 3;
+  const int nsamp = T.small ? min(T.spt, B - T.b0) : 1;
+  const int p_tile = T.small ? 0 : (T.tok0 < T.nxy ? 0 : 1 + (T.tok0 - T.nxy) / T.npl);
+  const int nsp = T.small ? nsamp * (per_plane ? 3 : 1) : 1;
+  const int tid = threadIdx.x;
+  if (S.mode == DS_NORM_CSUM) {
+    for (int idx = tid; idx < nsp * 256; idx += nthreads) {      // 8 lanes per (sp, group); whole warps in or out
+      const int l8 = idx & 7, sgi = idx >> 3, sp = sgi >> 5, grp = sgi & 31;
+      const int sl = T.small ? (per_plane ? sp / 3 : sp) : 0;
+      const int p = T.small ? (per_plane ? sp - sl * 3 : 0) : p_tile;
+      const int b = T.b0 + sl;
+      double sm = 0.0, ss = 0.0;
+      for (int ci = l8; ci < cpg; ci += 8) {
+        const int c = grp * cpg + ci;
+        const double* cs; int Cs, cc;
+        if (c < S.C0) { cs = S.csum0; Cs = S.C0; cc = c; } else { cs = S.csum1; Cs = S.C1; cc = c - S.C0; }
+        if (S.joint) {
+          const double2 q0 = *reinterpret_cast<const double2*>(cs + (((size_t)b * 3 + 0) * Cs + cc) * 2);
+          const double2 q1 = *reinterpret_cast<const double2*>(cs + (((size_t)b * 3 + 1) * Cs + cc) * 2);
+          const double2 q2 = *reinterpret_cast<const double2*>(cs + (((size_t)b * 3 + 2) * Cs + cc) * 2);
+          sm += q0.x + q1.x + q2.x; ss += q0.y + q1.y + q2.y;
+        } else {
+          const double2 q0 = *reinterpret_cast<const double2*>(cs + (((size_t)b * 3 + p) * Cs + cc) * 2);
+          sm += q0.x; ss += q0.y;
+        }
+      }
+#pragma unroll
+      for (int off = 4; off > 0; off >>= 1) { sm += __shfl_xor_sync(0xffffffffu, sm, off); ss += __shfl_xor_sync(0xffffffffu, ss, off); }
+      if (l8 == 0) {
+        const double cnt = (double)cpg * (S.joint ? (double)gs.L : (double)(p == 0 ? gs.res * gs.res : gs.t * gs.res));
+        const double mean = sm / cnt;
+        double var = ss / cnt - mean * mean; var = var < 0.0 ? 0.0 : var;
+        scratch[2 * sgi] = mean; scratch[2 * sgi + 1] = rsqrt(var + 1e-5);
+      }
+    }
+    __syncthreads();
+    for (int e = tid; e < nsp * C; e += nthreads) {
+      const int sp = e / C, c = e - sp * C;
+      const int sl = T.small ? (per_plane ? sp / 3 : sp) : 0;
+      const int b = T.b0 + sl;
+      const int grp = c / cpg;
+      double a = scratch[2 * (sp * 32 + grp) + 1] * (double)__ldg(S.gamma + c);
+      double d = (double)__ldg(S.beta + c) - scratch[2 * (sp * 32 + grp)] * a;
+      if (S.film) {
+        const float* f = S.film + (size_t)b * S.film_stride;
+        const double sc = 1.0 + (double)__ldg(f + c);
+        a *= sc; d = d * sc + (double)__ldg(f + C + c);
+      }
+      tbl[e] = make_float2((float)a, (float)d);
+    }
+  } else {   // DS_NORM_TABLE
+    for (int e = tid; e < nsp * C; e += nthreads) {
+      const int sp = e / C, c = e - sp * C;
+      const int sl = T.small ? (per_plane ? sp / 3 : sp) : 0;
+      const int p = T.small ? (per_plane ? sp - sl * 3 : 0) : p_tile;
+      const size_t ni = ((size_t)(T.b0 + sl) * S.nrm_nseg + (per_plane ? p : 0)) * C + c;
+      tbl[e] = make_float2(__ldg(S.nrm_a + ni), __ldg(S.nrm_d + ni));
+    }
+  }
+}
+
+// 8 transformed channels -> split bf16 (hi, lo), packed for one 16-byte operand chunk each
+__device__ __forceinline__ uint32_t tc_cvt_bf16x2(float lo_elem, float hi_elem) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
+  return r;
+}
+__device__ __forceinline__ void tc_pack_split8(const float (&y)[8], uint4& hi, uint4& lo) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    h[i] = tc_cvt_bf16x2(y[2 * i], y[2 * i + 1]);
+    l[i] = tc_cvt_bf16x2(y[2 * i] - __uint_as_float(h[i] << 16), y[2 * i + 1] - __uint_as_float(h[i] & 0xffff0000u));
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]); lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// A-operand producer of the direct mode.  Two groups of four warps alternate K-iterations (group = parity of the
+// iteration within this CTA's range), so one group's global-load latency hides behind the other's arithmetic.
+// Thread (tg) of a group owns the 16-byte chunk `sub` = tg & 7 (8 channels) of rows (tg >> 3) + 16k, k = 0..7:
+// coalesced 256-byte row segments in, conflict-free 128B-swizzled chunks out (chunk c of row r at c ^ (r & 7)).
+// The loops stay rolled (4 rows per trip): fully unrolled, the body outgrows the instruction cache and the producers
+// run several times slower than the tensor pipe.
+// rowinfo[r] = (sample within tile << 16) | (plane << 12) | (y << 6) | x of tile row r, or -1 beyond the batch.
+template <int BN>
+__device__ __forceinline__ void tc_produce_A(const TcConvParams& P, const Geo& g, const TcTile& T, int it0, int it1, int it_main, int kch,
+                                             uint32_t smem0, uint64_t* bar_full, uint64_t* bar_empty, const float2* tbl,
+                                             const int* rowinfo, int group, int tg, long long* pstamp) {
+  constexpr int NS = tc_stages(BN);
+  constexpr int STAGE = tc_stage_bytes(BN);
+  const int lane = threadIdx.x & 31;
+  const int sub = tg & 7, rbase = tg >> 3;
+  int stage = 0; uint32_t phase = 0;
+#pragma unroll 1
+  for (int it = it0; it < it1; ++it) {
+    if (((it - it0) & 1) == group) {
+      const bool seg1 = it >= it_main;
+      const DirectSeg& S = P.dseg[seg1 ? 1 : 0];
+      const int tap = seg1 ? 0 : it / kch;
+      const int c0 = seg1 ? (it - it_main) * TC_BK : (it - tap * kch) * TC_BK;
+      const int ntaps = seg1 ? 1 : P.taps;
+      const int dy = ntaps == 1 ? 0 : tap / 3 - 1, dx = ntaps == 1 ? 0 : tap - (tap / 3) * 3 - 1;
+      const int C = S.C0 + S.C1;
+      const float* src; int Cs, cc;
+      if (c0 < S.C0) { src = S.src0; Cs = S.C0; cc = c0; } else { src = S.src1; Cs = S.C1; cc = c0 - S.C0; }
+      cc += sub * 8;
+      const bool normed = S.mode >= DS_NORM_CSUM;
+      const bool per_plane = S.mode == DS_NORM_CSUM ? !S.joint : S.nrm_nseg == 3;
+      const bool silu = S.silu != 0;
+      const int resample = S.resample;
+      const Geo gs = resample == RS_NONE ? g : (resample == RS_UP2 ? geo_down(g) : geo_up(g));
+      const uint32_t sA_hi = smem0 + stage * STAGE, sA_lo = sA_hi + TC_BM * 128;
+      const float2* tcol = tbl + c0 + sub * 8;
+      auto xf8 = [&](const float4& w0, const float4& w1, const float2* te, float (&y)[8]) {
+        y[0] = w0.x; y[1] = w0.y; y[2] = w0.z; y[3] = w0.w; y[4] = w1.x; y[5] = w1.y; y[6] = w1.z; y[7] = w1.w;
+        if (normed) {
+#pragma unroll
+          for (int i = 0; i < 8; i += 2) {
+            const float4 ad = *reinterpret_cast<const float4*>(te + i);     // a_i, d_i, a_{i+1}, d_{i+1}
+            y[i] = fmaf(y[i], ad.x, ad.y); y[i + 1] = fmaf(y[i + 1], ad.z, ad.w);
+          }
+        }
+        if (silu) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) y[i] = silu_tc(y[i]);
+        }
+      };
+      // source element offset of tile row `ri` shifted by this tap, or -1 (zero padding / beyond the batch)
+      auto locate = [&](int ri, int& sp) -> long long {
+        if (ri < 0) return -1;
+        const int bl = ri >> 16, p = (ri >> 12) & 3, yy = ((ri >> 6) & 63) + dy, xx = (ri & 63) + dx;
+        const int Hp = p == 0 ? g.res : g.t;
+        if (yy < 0 || yy >= Hp || xx < 0 || xx >= g.res) return -1;
+        sp = T.small ? (per_plane ? bl * 3 + p : bl) : 0;
+        const int ts = resample == RS_NONE ? tc_plane_off(g, p) + yy * g.res + xx
+                     : (resample == RS_UP2 ? tc_plane_off(gs, p) + (yy >> 1) * gs.res + (xx >> 1)
+                                           : tc_plane_off(gs, p) + (2 * yy) * gs.res + 2 * xx);
+        return ((long long)(T.b0 + bl) * gs.L + ts) * Cs + cc;
+      };
+      const int pj = (it - it0) >> 1;
+      const bool stampit = pstamp != nullptr && group == 0 && tg == 0 && pj < 4;
+      if (stampit) pstamp[4 * pj] = clock64();
+      mbar_wait(&bar_empty[stage], phase ^ 1u);
+      if (stampit) pstamp[4 * pj + 1] = clock64();
+      if (resample != RS_DOWN2) {
+#pragma unroll 1
+        for (int kb = 0; kb < 8; kb += 4) {
+          float4 w[4][2]; int sp[4]; bool ok[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            sp[j] = 0;
+            const long long off = locate(rowinfo[rbase + 16 * (kb + j)], sp[j]);
+            ok[j] = off >= 0;
+            if (ok[j]) {
+              w[j][0] = __ldg(reinterpret_cast<const float4*>(src + off)); w[j][1] = __ldg(reinterpret_cast<const float4*>(src + off + 4));
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int r = rbase + 16 * (kb + j);
+            uint4 hi = make_uint4(0u, 0u, 0u, 0u), lo = hi;
+            if (ok[j]) {
+              float y[8]; xf8(w[j][0], w[j][1], tcol + (size_t)sp[j] * C, y);
+              tc_pack_split8(y, hi, lo);
+            }
+            const uint32_t off = (uint32_t)r * 128u + (uint32_t)((sub ^ (r & 7)) << 4);
+            st_shared_v4(sA_hi + off, hi); st_shared_v4(sA_lo + off, lo);
+          }
+        }
+      } else {
+        // avg-pool 2x2 of the TRANSFORMED source (ResBlock h_upd after GroupNorm+SiLU, unet.py:181-182; raw x for the skip)
+#pragma unroll 1
+        for (int k = 0; k < 8; ++k) {
+          const int r = rbase + 16 * k;
+          int sp = 0;
+          const long long off = locate(rowinfo[r], sp);
+          uint4 hi = make_uint4(0u, 0u, 0u, 0u), lo = hi;
+          if (off >= 0) {
+            const float* q = src + off;
+            float4 w[4][2];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float* qj = q + (size_t)((j >> 1) * gs.res + (j & 1)) * Cs;
+              w[j][0] = __ldg(reinterpret_cast<const float4*>(qj)); w[j][1] = __ldg(reinterpret_cast<const float4*>(qj + 4));
+            }
+            float acc[8], v[8];
+            xf8(w[0][0], w[0][1], tcol + (size_t)sp * C, acc);
+            xf8(w[1][0], w[1][1], tcol + (size_t)sp * C, v);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] += v[i];
+            float u[8];
+            xf8(w[2][0], w[2][1], tcol + (size_t)sp * C, u);
+            xf8(w[3][0], w[3][1], tcol + (size_t)sp * C, v);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] = 0.25f * (acc[i] + (u[i] + v[i]));
+            tc_pack_split8(acc, hi, lo);
+          }
+          const uint32_t soff = (uint32_t)r * 128u + (uint32_t)((sub ^ (r & 7)) << 4);
+          st_shared_v4(sA_hi + soff, hi); st_shared_v4(sA_lo + soff, lo);
+        }
+      }
+      if (stampit) pstamp[4 * pj + 2] = clock64();
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA (async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_full[stage]);
+      if (stampit) pstamp[4 * pj + 3] = clock64();
+    }
+    if (++stage == NS) { stage = 0; phase ^= 1u; }
   }
 }
 
@@ -720,8 +951,12 @@ __device__ __forceinline__ void tc_epilogue(const TcConvParams& P, const Geo& g,
 // paths a launch cannot take must not even be predicated off):
 //   0 split-K partial tile, 1 bias [+ same-geometry residual] [+ GroupNorm sums], 2 qkv operand split,
 //   3 residual through nearest-up / avg-pool geometry (up / down ResBlocks with identity skip)
-template <int BN, int EPI>
-__global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant__ TcConvParams P) {
+//
+// DIRECT: the A operand is produced in-kernel from the fp32 activation (tc_produce_A: GroupNorm affine + FiLM + SiLU +
+// resample + concat, split to bf16) by warps 2-9 instead of being fetched by TMA from a pre-split copy; warp 0 then only
+// streams the weights, and the four epilogue warps double as producers while the main loop runs.
+template <int BN, int EPI, bool DIRECT>
+__global__ void __launch_bounds__(DIRECT ? TC_THREADS_DIRECT : TC_THREADS, 1) k_conv_tc(const __grid_constant__ TcConvParams P) {
   constexpr int NS = tc_stages(BN);
   constexpr int STAGE = tc_stage_bytes(BN);
   // Stacked-N: W_hi and W_lo tiles are adjacent in smem, so ONE MMA with N = 2*BN computes
@@ -734,10 +969,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
   __shared__ __align__(8) uint64_t bar_full[NS], bar_empty[NS], bar_acc;
   __shared__ uint32_t tmem_base_s;
   __shared__ long long s_stamp[8];
+  __shared__ long long s_pstamp[DIRECT ? 16 : 1];  // diagnostics: producer-phase stamps of the first iterations
   __shared__ __align__(16) float s_bias[128];      // this CTA's BN bias values, fetched while the main loop runs
+  __shared__ int s_rowinfo[DIRECT ? TC_BM : 1];    // direct mode: (sample, plane, y, x) of every tile row
   const bool dbg = g_tc_dbg != nullptr;
   long long g_t0 = 0;
-  if (dbg && threadIdx.x == 0) { s_stamp[0] = clock64(); g_t0 = gtime_ns(); }
+  if (dbg && threadIdx.x == 0) { s_stamp[0] = clock64(); g_t0 = gtime_ns(); if (DIRECT) for (int i = 0; i < 16; ++i) s_pstamp[i] = 0; }
+  mtv_prefetch_slice(P.pf0, P.pf1, P.pf_bytes, blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z),
+                     gridDim.x * gridDim.y * gridDim.z);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B tiles need 1024-B alignment
@@ -757,11 +996,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
   }
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < NS; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
+    // full barrier: the TMA thread's expect_tx arrival (+ one arrival per producer warp of the owning group when DIRECT)
+    for (int s = 0; s < NS; ++s) { mbar_init(&bar_full[s], DIRECT ? 5 : 1); mbar_init(&bar_empty[s], 1); }
     mbar_init(&bar_acc, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    prefetch_tmap(&P.tmA_hi[0]); prefetch_tmap(&P.tmA_lo[0]); prefetch_tmap(&P.tmW_hi); prefetch_tmap(&P.tmW_lo);
+    if (!DIRECT) { prefetch_tmap(&P.tmA_hi[0]); prefetch_tmap(&P.tmA_lo[0]); }
+    prefetch_tmap(&P.tmW_hi); prefetch_tmap(&P.tmW_lo);
   }
   if (warp == 1) {   // TMEM: BN fp32 accumulator columns x 128 lanes
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"((uint32_t)(2 * BN)) : "memory");
@@ -772,23 +1013,44 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
   if (dbg && threadIdx.x == 0) s_stamp[1] = clock64();
+  constexpr uint32_t TX_BYTES = DIRECT ? (uint32_t)(2 * BN * 128) : (uint32_t)STAGE;   // bytes TMA delivers per stage
+  const int npre = min(NS, it1 - it0);
+  const float2* tbl = reinterpret_cast<const float2*>(smem_raw + (smem0 - smem_u32(smem_raw)) + NS * STAGE);
+
+  auto load_W = [&](int it, int stage) {
+    const uint32_t sW_hi = smem0 + stage * STAGE + 2 * TC_BM * 128, sW_lo = sW_hi + BN * 128;
+    const uint32_t fb = smem_u32(&bar_full[stage]);
+    if (it >= it_main) {
+      const int c2 = (it - it_main) * TC_BK;
+      tma_load_2d(sW_hi, &P.tmW2_hi, fb, c2, n0);
+      tma_load_2d(sW_lo, &P.tmW2_lo, fb, c2, n0);
+    } else {
+      const int tap = it / kch, c0 = (it - tap * kch) * TC_BK;
+      tma_load_2d(sW_hi, &P.tmW_hi, fb, c0, tap * P.Cout + n0);
+      tma_load_2d(sW_lo, &P.tmW_lo, fb, c0, tap * P.Cout + n0);
+    }
+  };
+  if constexpr (DIRECT) {
+    // weights first (they do not depend on the previous kernel), then the whole CTA turns the producers' channel sums
+    // into this tile's affine table while those loads are in flight
+    if (threadIdx.x == 0) {
+      for (int i = 0; i < npre; ++i) { mbar_expect_tx(&bar_full[i], TX_BYTES); load_W(it0 + i, i); }
+    }
+    if (threadIdx.x < TC_BM) {
+      int b, tok; tc_row_map(T, (int)threadIdx.x, b, tok);
+      int p, y, x; tc_decode_fast(T, tok, p, y, x);
+      s_rowinfo[threadIdx.x] = b < P.B ? (((b - T.b0) << 16) | (p << 12) | (y << 6) | x) : -1;
+    }
+    MTV_PDL_WAIT();
+    if (P.dseg[0].mode >= DS_NORM_CSUM)
+      tc_build_table(P.dseg[0], g, T, P.B, const_cast<float2*>(tbl), reinterpret_cast<double*>(smem_raw + (smem0 - smem_u32(smem_raw))),
+                     TC_THREADS_DIRECT);
+    __syncthreads();
+  }
 
   if (warp == 0) {
     // =============================== TMA producer ===============================
     if (lane == 0) {
-      auto load_W = [&](int it, int stage) {
-        const uint32_t sW_hi = smem0 + stage * STAGE + 2 * TC_BM * 128, sW_lo = sW_hi + BN * 128;
-        const uint32_t fb = smem_u32(&bar_full[stage]);
-        if (it >= it_main) {
-          const int c2 = (it - it_main) * TC_BK;
-          tma_load_2d(sW_hi, &P.tmW2_hi, fb, c2, n0);
-          tma_load_2d(sW_lo, &P.tmW2_lo, fb, c2, n0);
-        } else {
-          const int tap = it / kch, c0 = (it - tap * kch) * TC_BK;
-          tma_load_2d(sW_hi, &P.tmW_hi, fb, c0, tap * P.Cout + n0);
-          tma_load_2d(sW_lo, &P.tmW_lo, fb, c0, tap * P.Cout + n0);
-        }
-      };
       auto load_A = [&](int it, int stage) {
         const uint32_t sA_hi = smem0 + stage * STAGE, sA_lo = sA_hi + TC_BM * 128;
         const uint32_t fb = smem_u32(&bar_full[stage]);
@@ -801,21 +1063,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
       };
       // Weights do not depend on the previous kernel: fill the ring's W halves BEFORE the grid
       // dependency resolves (overlaps their HBM latency with the predecessor's tail) ...
-      const int npre = min(NS, it1 - it0);
-      for (int i = 0; i < npre; ++i) {
-        mbar_expect_tx(&bar_full[i], (uint32_t)STAGE);
-        load_W(it0 + i, i);
+      if constexpr (!DIRECT) {
+        for (int i = 0; i < npre; ++i) {
+          mbar_expect_tx(&bar_full[i], TX_BYTES);
+          load_W(it0 + i, i);
+        }
+        MTV_PDL_WAIT();                // ... the activation operand does
       }
-      MTV_PDL_WAIT();                  // ... the activation operand does
       int stage = 0; uint32_t phase = 0;
       for (int it = it0; it < it1; ++it) {
         if (it - it0 >= npre) {
           mbar_wait(&bar_empty[stage], phase ^ 1u);
-          mbar_expect_tx(&bar_full[stage], (uint32_t)STAGE);
+          mbar_expect_tx(&bar_full[stage], TX_BYTES);
           load_W(it, stage);
         }
         if (dbg && it == it1 - 1) s_stamp[2] = clock64();          // last stage request issued
-        load_A(it, stage);
+        if constexpr (!DIRECT) load_A(it, stage);
         if (++stage == NS) { stage = 0; phase ^= 1u; }
       }
     }
@@ -850,7 +1113,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
     mbar_wait(&bar_acc, 0);
     MTV_PDL_TRIGGER();
   } else {
-    tc_epilogue<BN, EPI, true>(P, g, T, n0, (int)blockIdx.z, tmem_base, s_bias, &bar_acc, 0u, dbg ? s_stamp : nullptr);
+    if constexpr (DIRECT) {
+      const int pw = warp - 2;                    // producer warp 0..7: group = pw >> 2
+      tc_produce_A<BN>(P, g, T, it0, it1, it_main, kch, smem0, bar_full, bar_empty, tbl, s_rowinfo, pw >> 2, (pw & 3) * 32 + lane, dbg ? s_pstamp : nullptr);
+    }
+    if (!DIRECT || warp < 6) {
+      tc_epilogue<BN, EPI, true>(P, g, T, n0, (int)blockIdx.z, tmem_base, s_bias, &bar_acc, 0u, dbg ? s_stamp : nullptr);
+    } else {
+      mbar_wait(&bar_acc, 0);
+      MTV_PDL_TRIGGER();
+    }
   }
   if (dbg && threadIdx.x == 64) s_stamp[6] = clock64();              // epilogue stores issued
   tc_fence_before();
@@ -869,6 +1141,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
       rec[9] = clock64(); rec[10] = g_t0; rec[11] = gtime_ns();
       unsigned int smid; asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
       rec[12] = smid; rec[13] = (long long)blockIdx.x | ((long long)blockIdx.y << 16) | ((long long)blockIdx.z << 32);
+      if (DIRECT) {
+        const unsigned int slot2 = atomicAdd(&g_tc_dbg_count, 1u);
+        if (slot2 < g_tc_dbg_cap) {
+          long long* r2 = g_tc_dbg + (size_t)slot2 * 16;
+          r2[0] = (1ll << 61) | rec[0]; r2[1] = rec[1]; r2[2] = s_stamp[0];
+          for (int i = 0; i < 12; ++i) r2[3 + i] = s_pstamp[i];
+        }
+      }
     }
   }
 }
@@ -1281,9 +1561,15 @@ cudaError_t launch_conv_tc(const TcConvParams& P, cudaStream_t s) {
   const int epi = P.ksplit > 1 ? 0 : (P.qkv_heads ? 2 : ((P.resid && P.resid_mode != RS_NONE) ? 3 : 1));
 #define MTV_TC_LAUNCH(BN_, EPI_)                                                                                   \
   do {                                                                                                             \
-    e = cudaFuncSetAttribute(k_conv_tc<BN_, EPI_>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(BN_)); \
-    if (e != cudaSuccess) return e;                                                                                \
-    e = launch_kc(PDL_CLASS_CONV_TC, k_conv_tc<BN_, EPI_>, grid, dim3(TC_THREADS), (size_t)tc_smem_bytes(BN_), s, P);                   \
+    if (P.direct) {                                                                                                \
+      e = cudaFuncSetAttribute(k_conv_tc<BN_, EPI_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes_direct(BN_)); \
+      if (e != cudaSuccess) return e;                                                                              \
+      e = launch_kc(PDL_CLASS_CONV_TC, k_conv_tc<BN_, EPI_, true>, grid, dim3(TC_THREADS_DIRECT), (size_t)tc_smem_bytes_direct(BN_), s, P); \
+    } else {                                                                                                       \
+      e = cudaFuncSetAttribute(k_conv_tc<BN_, EPI_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(BN_)); \
+      if (e != cudaSuccess) return e;                                                                              \
+      e = launch_kc(PDL_CLASS_CONV_TC, k_conv_tc<BN_, EPI_, false>, grid, dim3(TC_THREADS), (size_t)tc_smem_bytes(BN_), s, P); \
+    }                                                                                                              \
     if (e != cudaSuccess) return e;                                                                                \
   } while (0)
   if (BN == 64) {

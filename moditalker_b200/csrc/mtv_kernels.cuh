@@ -24,7 +24,7 @@
 
 namespace mtv {
 
-// MTV_PDL is a bit mask of kernel classes launched with programmatic stream serialisation (default 1):
+// MTV_PDL is a bit mask of kernel classes launched with programmatic stream serialisation (default 5):
 //   1 tensor-core tap-GEMM (follows a short apply kernel that triggers at entry: setup, TMEM allocation and the
 //     weight TMA requests overlap that kernel, nothing is pre-launched more than one kernel deep)
 //   2 tensor-core attention, 4 apply kernels, 8 split-K reductions, 16 everything else

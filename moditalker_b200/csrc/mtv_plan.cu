@@ -163,7 +163,10 @@ struct MtvHandle_t {
   std::map<int, std::unique_ptr<Plan>> plans;
   Plan* last_plan = nullptr;
   int64_t weight_bytes = 0;
-  int tc_mask = 0xfff;      // bit 12 (persistent chain kernel) is opt-in: measured slower, profiles/r01_s2_chain_experiment.md
+  // feature bits (MTV_TC_MASK): 0-4 op classes on the tensor-core kernel, 5 split-K, 6 tcgen05 attention, 7 small levels,
+  // 8 fused GroupNorm statistics, 9 launch fusions, 10 weight L2 prefetch, 11 L2-persisting small-tensor arena;
+  // opt-in (measured slower on B200, kept for A/B — profiles/r01_s2_*.md): 12 persistent chain kernel, 13 direct A operand
+  int tc_mask = 0xfff;
   cudaStream_t cap_stream = nullptr;
   cudaStream_t capture_stream() {
     if (!cap_stream) CK(cudaStreamCreateWithFlags(&cap_stream, cudaStreamNonBlocking));
@@ -502,6 +505,35 @@ struct Builder {
       }
     }
   }
+  // ---- direct A operand (kernels_tc.cu: tc_produce_A): the GEMM's producer warps apply GroupNorm / FiLM / SiLU / resample /
+  // concat themselves, so neither the apply launch nor the split-bf16 copy of the activation exists.
+  bool use_direct() const { return h->cfg.kernel_path != 1 && ((h->tc_mask >> 13) & 1); }
+  bool direct_seg_ok(const KSeg& S, int norm_id, const Geo& g) const {
+    if (S.C0 % 64 || S.C1 % 64) return false;
+    if (norm_id < 0) return true;
+    const NormSpec& n = norms[norm_id];
+    const bool small = g.L <= 128;
+    const int spt = small ? std::min(128 / g.L, B) : 1;
+    const int nsp = small ? spt * (n.joint ? 1 : 3) : 1;
+    return (size_t)nsp * (S.C0 + S.C1) <= (size_t)TC_TABLE_ENTRIES;
+  }
+  DirectSeg make_direct_seg(const KSeg& S, int norm_id) {
+    DirectSeg D{};
+    D.src0 = S.src0; D.src1 = S.src1; D.C0 = S.C0; D.C1 = S.C1; D.silu = S.silu; D.resample = S.resample; D.mode = DS_RAW;
+    if (norm_id >= 0) {
+      const NormSpec& n = norms[norm_id];
+      D.gamma = n.gamma; D.beta = n.beta; D.joint = n.joint ? 1 : 0;
+      if (fuse_gn() && n.x0.csum && (!n.has_x1 || n.x1.csum)) {
+        D.mode = DS_NORM_CSUM; D.csum0 = n.x0.csum; D.csum1 = n.has_x1 ? n.x1.csum : nullptr;
+        if (n.film_off >= 0) { D.film = film_buf + n.film_off; D.film_stride = h->arch.J; }
+      } else {
+        const NormRef r = materialize(norm_id);       // FiLM is folded into the tables by k_gn_stats
+        D.mode = DS_NORM_TABLE; D.nrm_a = r.a; D.nrm_d = r.d; D.nrm_nseg = r.nseg;
+      }
+    }
+    return D;
+  }
+
   void conv_tc(const std::string& name, const ConvParams& P, int norm0, int norm1, Tensor* out_t, const TcOpts& o) {
     TcConvParams T{};
     if (out_t && fuse_gn()) { out_t->csum = alloc_csum(P.Cout); T.csum = out_t->csum; }
@@ -518,7 +550,12 @@ struct Builder {
     int bn = 64;
     if (P.Cout % 128 == 0 && mtiles * (P.Cout / 128) >= 64) bn = 128;   // fewer smem bytes per MMA once the SMs are covered
     T.bn = bn;
-    {
+    const bool direct = use_direct() && !o.pre0 && !o.pre1 && !o.raw_out && direct_seg_ok(S, norm0, P.geo) &&
+                        (P.nsegs == 1 || (norm1 < 0 && !P.seg[1].silu && direct_seg_ok(P.seg[1], -1, P.geo)));
+    if (direct) {
+      T.direct = 1;
+      T.dseg[0] = make_direct_seg(S, norm0);
+    } else {
       const SplitBuf a0 = o.pre0 ? *o.pre0 : emit_apply(name, S, P.geo, norm0, o.raw_out, S.w, P.Cout);
       make_A_maps(a0, T.Cin, S.taps, P.geo, T.tmA_hi, T.tmA_lo);
     }
@@ -535,17 +572,22 @@ struct Builder {
     if (P.nsegs == 2) {
       const KSeg& X = P.seg[1];
       T.Cin2 = X.C0 + X.C1;
-      const SplitBuf a1 = o.pre1 ? *o.pre1 : emit_apply(name + ".skip", X, P.geo, norm1, nullptr);
-      make_A_maps(a1, T.Cin2, 1, P.geo, T.tmA2_hi, T.tmA2_lo);
+      if (direct) {
+        T.dseg[1] = make_direct_seg(X, -1);
+      } else {
+        const SplitBuf a1 = o.pre1 ? *o.pre1 : emit_apply(name + ".skip", X, P.geo, norm1, nullptr);
+        make_A_maps(a1, T.Cin2, 1, P.geo, T.tmA2_hi, T.tmA2_lo);
+      }
       wmaps(X, T.tmW2_hi, T.tmW2_lo);
       Ktot += T.Cin2;
     }
     const int iters = T.taps * (T.Cin / 64) + T.Cin2 / 64;
     const int base = mtiles * (P.Cout / bn);
     int ks = 1;
-    if (iters >= 32 && ((h->tc_mask >> 5) & 1) && !o.qkv && base * 2 <= h->num_sms + h->num_sms / 4) {
-      // spread a fixed amount of shared-memory / weight traffic over (nearly) all SMs
-      ks = std::min(iters / 4, std::max(1, h->num_sms / base));
+    if (iters >= 16 && ((h->tc_mask >> 5) & 1) && !o.qkv && base * 2 <= h->num_sms + h->num_sms / 4) {
+      // spread a fixed amount of shared-memory / weight traffic over (nearly) all SMs; >= 3 K-iterations per CTA (a K-iteration
+      // is ~0.5 us at small batch, the extra reduction launch ~4 us: worth it from ~16 iterations up)
+      ks = std::min(iters / 3, std::max(1, h->num_sms / base));
       ks = std::min(ks, 32);
       while (ks > 1 && (ks - 1) * ((iters + ks - 1) / ks) >= iters) --ks;
     }
@@ -554,10 +596,31 @@ struct Builder {
     Op op; op.name = "conv_tc:" + name; op.launches = ks > 1 ? 2 : 1;
     op.flops = 2.0 * M * P.Cout * Ktot;
     op.bytes = 4.0 * Ktot * P.Cout + 4.0 * M * Ktot / S.taps + 4.0 * M * P.Cout;
-    op.fn = [T](cudaStream_t s) { return launch_conv_tc(T, s); };
-    op.ctype = CH_GEMM; op.tc = std::make_shared<TcConvParams>(T);
+    auto tp = std::make_shared<TcConvParams>(T);
+    op.fn = [tp](cudaStream_t s) { return launch_conv_tc(*tp, s); };
+    op.tc = tp;
+    tc_wptr[tp.get()] = h->tc_w.at(S.w);
+    if (!direct) op.ctype = CH_GEMM;
     pl->ops.push_back(op);
   }
+
+  // Weights are HBM-cold every step (529 MB stream through a 126 MB L2).  Each direct-mode tap-GEMM therefore asks L2 for
+  // the NEXT tap-GEMM's weights when it starts (the stand-alone apply kernel used to do this for its consumer).
+  void link_weight_prefetch() {
+    if (!((h->tc_mask >> 10) & 1)) return;
+    TcConvParams* prev = nullptr;
+    for (Op& op : pl->ops) {
+      if (!op.tc || op.phase != 1) continue;
+      TcConvParams* cur = op.tc.get();
+      if (prev && cur->direct) {          // a direct GEMM has no apply kernel in front of it to do this
+        // first K-segment's weights of `cur`: [taps][Cout][Cin] split pair, taken from its W tensor map's base
+        auto it = tc_wptr.find(cur);
+        if (it != tc_wptr.end()) { prev->pf0 = it->second.first; prev->pf1 = it->second.second; prev->pf_bytes = (unsigned long long)cur->taps * cur->Cin * cur->Cout * 2; }
+      }
+      prev = cur;
+    }
+  }
+  std::map<const TcConvParams*, std::pair<void*, void*>> tc_wptr;
 
   // Runs of consecutive chainable graph-body ops become ONE launch of the persistent chain kernel (kernels_tc.cu:
   // k_chain): kernel boundaries turn into grid-wide barriers, per-kernel prologues are paid once per chain.
@@ -655,7 +718,7 @@ struct Builder {
       P.bias = h->W(p + ".in_layers.2.bias"); P.out = hmid.p;
       // when both convs run on the tensor cores, conv1's apply kernel also emits the raw split of x that
       // conv2's fused 1x1 skip segment consumes (one launch instead of two)
-      if (r.cin != r.cout && fuse_launches() && tc_ok_pb(P)) {
+      if (r.cin != r.cout && fuse_launches() && !use_direct() && tc_ok_pb(P)) {
         ConvParams P2{}; P2.nsegs = 2; P2.geo = geo(level_out); P2.Cout = r.cout;
         P2.seg[0].C0 = r.cout; P2.seg[0].taps = 9; P2.seg[0].w = h->W(p + ".out_layers.3.weight");
         P2.seg[1].C0 = x0.C; P2.seg[1].C1 = x1 ? x1->C : 0; P2.seg[1].taps = 1; P2.seg[1].w = h->W(p + ".skip_connection.weight");
@@ -910,6 +973,7 @@ Plan* get_plan(MtvHandle_t* h, int B) {
   pl->B = B;
   Builder b(h, pl.get());
   b.build();
+  b.link_weight_prefetch();
   b.fuse_chains();
   CK(cudaDeviceSynchronize());   // memsets of the statistics scratch
   Plan* raw = pl.get();
@@ -1002,10 +1066,10 @@ int mtv_create(const MtvConfig* cfg, MtvHandle* out) {
     const char* ng = getenv("MTV_NO_GRAPH");
     h->use_graph = !(ng && ng[0] == '1');
     if (const char* tm = getenv("MTV_TC_MASK")) h->tc_mask = (int)strtol(tm, nullptr, 0);
-    // programmatic dependent launch, by kernel class (mtv_kernels.cuh).  Default: only the tensor-core tap-GEMM
-    // (measured on B200: -7.6 % step time at B=1, -3 % at B=8; enabling it for every kernel is a net loss because
-    // kernels pre-launched several deep contend with the running one)
-    { const char* np = getenv("MTV_PDL"); g_mtv_use_pdl = np ? atoi(np) : 1; }
+    // programmatic dependent launch, by kernel class (mtv_kernels.cuh).  Default: the tensor-core tap-GEMM and the apply
+    // kernels (measured on B200, B=1: none 2.59 ms, GEMM only 2.40, GEMM + apply 2.36, every kernel 2.50 — kernels
+    // pre-launched several deep contend with the running one)
+    { const char* np = getenv("MTV_PDL"); g_mtv_use_pdl = np ? atoi(np) : 5; }
     register_weights(h.get());
     *out = h.release();
   });

@@ -37,6 +37,21 @@ __device__ __forceinline__ void mtv_prefetch_slice(const void* p0, const void* p
   if (p1) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"((const char*)p1 + off), "r"(sz) : "memory");
 }
 
+// "Direct" A operand of one K-segment: instead of a pre-split bf16 tensor fetched by TMA, the GEMM's producer warps read
+// the fp32 activation(s), apply the GroupNorm affine (+FiLM) + SiLU + resample + channel concat themselves and write the
+// split-bf16 tile straight into the swizzled operand ring — the stand-alone apply pass (and its launch) disappears.
+enum { DS_TMA = 0, DS_RAW = 1, DS_NORM_CSUM = 2, DS_NORM_TABLE = 3 };
+struct DirectSeg {
+  const float* src0; const float* src1; int C0, C1;      // sources at the SOURCE geometry (see resample); C0, C1 % 64 == 0
+  const double* csum0; const double* csum1;               // DS_NORM_CSUM: producers' per-channel sums [B][3][C0|C1][2]
+  const float* nrm_a; const float* nrm_d; int nrm_nseg;   // DS_NORM_TABLE: affine tables of k_gn_stats [B][nseg][C]
+  const float* gamma; const float* beta;                  // [C0+C1]
+  const float* film; int film_stride;                     // FiLM row b = film + b*stride: scale[C] | shift[C]; nullptr: none
+  int joint;                                              // statistics over all three planes (AttentionBlock1D.norm)
+  int silu; int resample;                                 // RS_*: source geometry relative to the GEMM's geometry
+  int mode;                                               // DS_*
+};
+
 // D[B*L][Cout] = sum_tap A_tap[B*L][Cin] * W[tap][Cout][Cin]^T   (+bias, +residual)
 struct TcConvParams {
   // L > 128 : taps==9: [0] xy plane (C,W,H,B), [1] yt|xt planes (C,W,H,2,B), 128-token boxes; taps==1: [0] = (C, B*L)
@@ -57,7 +72,12 @@ struct TcConvParams {
   // split-bf16 Q (pre-scaled by log2(e)/sqrt(D)) and K as [B*H][L][D], V^T as [B*H][D][L]  (see k_qkv_split)
   int qkv_heads;
   void* q_hi; void* q_lo; void* k_hi; void* k_lo; void* vt_hi; void* vt_lo;
+  // direct mode (direct != 0): the A operands of BOTH K-segments are produced in-kernel (tmA_* unused)
+  int direct; DirectSeg dseg[2];
+  // L2 prefetch of the NEXT tap-GEMM's (HBM-cold) split weights, issued at kernel entry (one slice per CTA)
+  const void* pf0; const void* pf1; unsigned long long pf_bytes;
 };
+constexpr int TC_TABLE_ENTRIES = 3072;   // direct mode: (a, d) pairs per CTA = (sample-plane pairs of the tile) x channels
 
 // qkv fp32 [B][L][3C] -> split-bf16 Q (pre-scaled), K [B*H][L][D] and V^T [B*H][D][L]
 struct QkvSplitParams {

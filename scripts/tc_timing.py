@@ -39,6 +39,8 @@ _lib.check(lib.mtv_debug_tc_timing(h, None, 0, ctypes.byref(cnt)), "disarm")
 n = min(cnt.value, cap)
 rec = buf.cpu().view(cap, 16)[:n]
 rec = rec[(rec[:, 0] >> 62) == 0]          # chain-kernel records (scripts/chain_timing.py) carry bit 62
+prec = rec[(rec[:, 0] >> 61) == 1]         # direct-mode producer stamps
+rec = rec[(rec[:, 0] >> 61) == 0]
 print(f"{n} CTA records in one forward (B={B})")
 groups = defaultdict(list)
 for r in rec.tolist():
@@ -80,3 +82,21 @@ for i, L in enumerate(launches):
         print(f"{(L['t0'] - t_base) / 1e3:9.2f}  dur {dur:6.2f}  gap {gap:6.2f}  grid {(g0 & 0xffff)}x{(g0 >> 16) & 0xffff}x{(g0 >> 32) & 0xffff} iters {g1 & 0xffff} taps {(g1 >> 16) & 0xff} Cin {(g1 >> 24) & 0xffff} Cout {(g1 >> 40) & 0xffff}")
     prev_end = L["t1"]
 print(f"sum of TC launch durations {tot_dur:.1f} us; span {(launches[-1]['t1'] - t_base) / 1e3:.1f} us")
+
+# ---- direct-mode producer phases (group 0, thread 0): per iteration slot: wait for the ring slot, produce, fence+arrive
+if len(prec):
+    pg = defaultdict(list)
+    for r in prec.tolist():
+        pg[(r[0] & ~(1 << 61), r[1])].append(r)
+    print("\ndirect-mode producer phases, cycles (mean over CTAs): [start-of-iteration since kernel entry | wait | produce | fence+arrive] x first 3 iterations of group 0")
+    for (g0, g1), rs in pg.items():
+        gx, gy, gz = g0 & 0xffff, (g0 >> 16) & 0xffff, (g0 >> 32) & 0xffff
+        iters, taps, cin, cout = g1 & 0xffff, (g1 >> 16) & 0xff, (g1 >> 24) & 0xffff, (g1 >> 40) & 0xffff
+        out = []
+        for j in range(3):
+            ok = [r for r in rs if r[3 + 4 * j + 3] > 0]
+            if not ok:
+                continue
+            m = lambda f: sum(f(r) for r in ok) / len(ok)
+            out.append(f"[{m(lambda r: r[3 + 4 * j] - r[2]):7.0f} | {m(lambda r: r[4 + 4 * j] - r[3 + 4 * j]):6.0f} | {m(lambda r: r[5 + 4 * j] - r[4 + 4 * j]):6.0f} | {m(lambda r: r[6 + 4 * j] - r[5 + 4 * j]):5.0f}]")
+        print(f"grid {gx:3d}x{gy:2d}x{gz:2d} iters {iters:3d} taps {taps} Cin {cin:4d} Cout {cout:4d} n={len(rs):4d}  " + " ".join(out))
