@@ -563,8 +563,8 @@ __device__ __forceinline__ void tc_csum_chunk32(float (&v)[32], bool live, int l
 
 // ------------------------------------------------------------------ direct A operand (no apply pass)
 // sample-plane slot of a tile row in the affine table
-__device__ __forceinline__ int tc_sp_index(const TcTile& T, bool per_plane, int b, int p) {
-  return T.small ? (per_plane ? (b - T.b0) * 3 + p : (b - T.b0)) : 0;
+__device__ __forceinline__ int tc_sp_index_local(const TcTile& T, bool per_plane, int sample_in_tile, int p) {
+  return T.small ? (per_plane ? sample_in_tile * 3 + p : sample_in_tile) : 0;
 }
 
 // Affine table of one K-segment for this CTA's tile: tbl[sp][c] = (a, d) with y = x*a + d the GroupNorm (+FiLM) of channel c
@@ -654,16 +654,50 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, const uint4& v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
-// A-operand producer of the direct mode.  Two groups of four warps alternate K-iterations (group = parity of the
-// iteration within this CTA's range), so one group's global-load latency hides behind the other's arithmetic.
-// Thread (tg) of a group owns the 16-byte chunk `sub` = tg & 7 (8 channels) of rows (tg >> 3) + 16k, k = 0..7:
-// coalesced 256-byte row segments in, conflict-free 128B-swizzled chunks out (chunk c of row r at c ^ (r & 7)).
-// The loops stay rolled (4 rows per trip): fully unrolled, the body outgrows the instruction cache and the producers
-// run several times slower than the tensor pipe.
-// rowinfo[r] = (sample within tile << 16) | (plane << 12) | (y << 6) | x of tile row r, or -1 beyond the batch.
+__device__ __forceinline__ float4 ld_shared_v4f(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
+// One fp32 A tile (128 rows x 64 channels, 256-byte rows, unswizzled) of K-chunk c0 of tap `tap` from ONE source tensor —
+// same boxes / coordinates as tc_load_A, fp32 tensor maps: m[0] = xy plane (or the 2-D / 3-D map when taps == 1), m[1] = planes.
+__device__ __forceinline__ void tc_load_A32(const Geo& g, const TcTile& t, const CUtensorMap* m, int taps, int tap, int c0,
+                                            uint32_t sA, uint32_t fb) {
+  if (!t.small) {
+    if (taps == 1) { tma_load_2d(sA, &m[0], fb, c0, t.b0 * g.L + t.tok0); return; }
+    const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
+    if (t.tok0 < t.nxy) {
+      tma_load_4d(sA, &m[0], fb, c0, dx, t.tok0 / g.res + dy, t.b0);
+    } else {
+      const int r = t.tok0 - t.nxy;
+      const int pl = r / t.npl, y0 = (r - pl * t.npl) / g.res;
+      tma_load_5d(sA, &m[1], fb, c0, dx, y0 + dy, pl, t.b0);
+    }
+    return;
+  }
+  const uint32_t o1 = (uint32_t)(t.spt * t.nxy) * 256u, o2 = o1 + (uint32_t)(t.spt * t.npl) * 256u;
+  if (taps == 1) {
+    tma_load_3d(sA, &m[0], fb, c0, 0, t.b0);
+    tma_load_3d(sA + o1, &m[1], fb, c0, t.nxy, t.b0);
+    tma_load_3d(sA + o2, &m[1], fb, c0, t.nxy + t.npl, t.b0);
+  } else {
+    const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
+    tma_load_4d(sA, &m[0], fb, c0, dx, dy, t.b0);
+    tma_load_5d(sA + o1, &m[1], fb, c0, dx, dy, 0, t.b0);
+    tma_load_5d(sA + o2, &m[1], fb, c0, dx, dy, 1, t.b0);
+  }
+}
+
+// A-operand producer of the direct mode.  TMA lands the RAW fp32 tile (shifted box of this tap, zero fill outside the
+// plane) in the stage's A region; a group of four warps then converts it IN PLACE into the split-bf16 operand pair:
+// read own 8 channels of 8 rows into registers -> group barrier (every read done) -> y = silu?(x*a + d) -> hi / lo chunks
+// written 128B-swizzled (chunk c of row r at c ^ (r & 7)) over the same 32 KB.  Two groups alternate K-iterations.
+// Rows whose tap falls outside the plane must stay ZERO after the transform (the conv pads the normalised activation),
+// hence the (row, tap) validity test from rowinfo[r] = (sample in tile << 16) | (plane << 12) | (y << 6) | x, or -1.
 template <int BN>
 __device__ __forceinline__ void tc_produce_A(const TcConvParams& P, const Geo& g, const TcTile& T, int it0, int it1, int it_main, int kch,
-                                             uint32_t smem0, uint64_t* bar_full, uint64_t* bar_empty, const float2* tbl,
+                                             uint32_t smem0, uint64_t* bar_raw, uint64_t* bar_full, const float2* tbl,
                                              const int* rowinfo, int group, int tg, long long* pstamp) {
   constexpr int NS = tc_stages(BN);
   constexpr int STAGE = tc_stage_bytes(BN);
@@ -680,103 +714,48 @@ __device__ __forceinline__ void tc_produce_A(const TcConvParams& P, const Geo& g
       const int ntaps = seg1 ? 1 : P.taps;
       const int dy = ntaps == 1 ? 0 : tap / 3 - 1, dx = ntaps == 1 ? 0 : tap - (tap / 3) * 3 - 1;
       const int C = S.C0 + S.C1;
-      const float* src; int Cs, cc;
-      if (c0 < S.C0) { src = S.src0; Cs = S.C0; cc = c0; } else { src = S.src1; Cs = S.C1; cc = c0 - S.C0; }
-      cc += sub * 8;
       const bool normed = S.mode >= DS_NORM_CSUM;
       const bool per_plane = S.mode == DS_NORM_CSUM ? !S.joint : S.nrm_nseg == 3;
       const bool silu = S.silu != 0;
-      const int resample = S.resample;
-      const Geo gs = resample == RS_NONE ? g : (resample == RS_UP2 ? geo_down(g) : geo_up(g));
-      const uint32_t sA_hi = smem0 + stage * STAGE, sA_lo = sA_hi + TC_BM * 128;
+      const uint32_t sA = smem0 + stage * STAGE;
       const float2* tcol = tbl + c0 + sub * 8;
-      auto xf8 = [&](const float4& w0, const float4& w1, const float2* te, float (&y)[8]) {
-        y[0] = w0.x; y[1] = w0.y; y[2] = w0.z; y[3] = w0.w; y[4] = w1.x; y[5] = w1.y; y[6] = w1.z; y[7] = w1.w;
-        if (normed) {
-#pragma unroll
-          for (int i = 0; i < 8; i += 2) {
-            const float4 ad = *reinterpret_cast<const float4*>(te + i);     // a_i, d_i, a_{i+1}, d_{i+1}
-            y[i] = fmaf(y[i], ad.x, ad.y); y[i + 1] = fmaf(y[i + 1], ad.z, ad.w);
-          }
-        }
-        if (silu) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) y[i] = silu_tc(y[i]);
-        }
-      };
-      // source element offset of tile row `ri` shifted by this tap, or -1 (zero padding / beyond the batch)
-      auto locate = [&](int ri, int& sp) -> long long {
-        if (ri < 0) return -1;
-        const int bl = ri >> 16, p = (ri >> 12) & 3, yy = ((ri >> 6) & 63) + dy, xx = (ri & 63) + dx;
-        const int Hp = p == 0 ? g.res : g.t;
-        if (yy < 0 || yy >= Hp || xx < 0 || xx >= g.res) return -1;
-        sp = T.small ? (per_plane ? bl * 3 + p : bl) : 0;
-        const int ts = resample == RS_NONE ? tc_plane_off(g, p) + yy * g.res + xx
-                     : (resample == RS_UP2 ? tc_plane_off(gs, p) + (yy >> 1) * gs.res + (xx >> 1)
-                                           : tc_plane_off(gs, p) + (2 * yy) * gs.res + 2 * xx);
-        return ((long long)(T.b0 + bl) * gs.L + ts) * Cs + cc;
-      };
       const int pj = (it - it0) >> 1;
       const bool stampit = pstamp != nullptr && group == 0 && tg == 0 && pj < 4;
       if (stampit) pstamp[4 * pj] = clock64();
-      mbar_wait(&bar_empty[stage], phase ^ 1u);
+      mbar_wait(&bar_raw[stage], phase);                   // the raw fp32 tile has landed
       if (stampit) pstamp[4 * pj + 1] = clock64();
-      if (resample != RS_DOWN2) {
-#pragma unroll 1
-        for (int kb = 0; kb < 8; kb += 4) {
-          float4 w[4][2]; int sp[4]; bool ok[4];
+      float4 w[8][2];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            sp[j] = 0;
-            const long long off = locate(rowinfo[rbase + 16 * (kb + j)], sp[j]);
-            ok[j] = off >= 0;
-            if (ok[j]) {
-              w[j][0] = __ldg(reinterpret_cast<const float4*>(src + off)); w[j][1] = __ldg(reinterpret_cast<const float4*>(src + off + 4));
+      for (int k = 0; k < 8; ++k) {
+        const uint32_t a = sA + (uint32_t)(rbase + 16 * k) * 256u + (uint32_t)sub * 32u;
+        w[k][0] = ld_shared_v4f(a); w[k][1] = ld_shared_v4f(a + 16u);
+      }
+      asm volatile("bar.sync %0, 128;" ::"r"(2 + group) : "memory");   // every thread of the group holds its part: overwrite in place
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int r = rbase + 16 * k;
+        const int ri = rowinfo[r];
+        const int p = (ri >> 12) & 3, yy = ((ri >> 6) & 63) + dy, xx = (ri & 63) + dx;
+        const bool ok = ri >= 0 && yy >= 0 && yy < (p == 0 ? g.res : g.t) && xx >= 0 && xx < g.res;
+        uint4 hi = make_uint4(0u, 0u, 0u, 0u), lo = hi;
+        if (ok) {
+          float y[8] = {w[k][0].x, w[k][0].y, w[k][0].z, w[k][0].w, w[k][1].x, w[k][1].y, w[k][1].z, w[k][1].w};
+          if (normed) {
+            const float2* te = tcol + (size_t)tc_sp_index_local(T, per_plane, ri >> 16, p) * C;
+#pragma unroll
+            for (int i = 0; i < 8; i += 2) {
+              const float4 ad = *reinterpret_cast<const float4*>(te + i);     // a_i, d_i, a_{i+1}, d_{i+1}
+              y[i] = fmaf(y[i], ad.x, ad.y); y[i + 1] = fmaf(y[i + 1], ad.z, ad.w);
             }
           }
+          if (silu) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int r = rbase + 16 * (kb + j);
-            uint4 hi = make_uint4(0u, 0u, 0u, 0u), lo = hi;
-            if (ok[j]) {
-              float y[8]; xf8(w[j][0], w[j][1], tcol + (size_t)sp[j] * C, y);
-              tc_pack_split8(y, hi, lo);
-            }
-            const uint32_t off = (uint32_t)r * 128u + (uint32_t)((sub ^ (r & 7)) << 4);
-            st_shared_v4(sA_hi + off, hi); st_shared_v4(sA_lo + off, lo);
+            for (int i = 0; i < 8; ++i) y[i] = silu_tc(y[i]);
           }
+          tc_pack_split8(y, hi, lo);
         }
-      } else {
-        // avg-pool 2x2 of the TRANSFORMED source (ResBlock h_upd after GroupNorm+SiLU, unet.py:181-182; raw x for the skip)
-#pragma unroll 1
-        for (int k = 0; k < 8; ++k) {
-          const int r = rbase + 16 * k;
-          int sp = 0;
-          const long long off = locate(rowinfo[r], sp);
-          uint4 hi = make_uint4(0u, 0u, 0u, 0u), lo = hi;
-          if (off >= 0) {
-            const float* q = src + off;
-            float4 w[4][2];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float* qj = q + (size_t)((j >> 1) * gs.res + (j & 1)) * Cs;
-              w[j][0] = __ldg(reinterpret_cast<const float4*>(qj)); w[j][1] = __ldg(reinterpret_cast<const float4*>(qj + 4));
-            }
-            float acc[8], v[8];
-            xf8(w[0][0], w[0][1], tcol + (size_t)sp * C, acc);
-            xf8(w[1][0], w[1][1], tcol + (size_t)sp * C, v);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) acc[i] += v[i];
-            float u[8];
-            xf8(w[2][0], w[2][1], tcol + (size_t)sp * C, u);
-            xf8(w[3][0], w[3][1], tcol + (size_t)sp * C, v);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) acc[i] = 0.25f * (acc[i] + (u[i] + v[i]));
-            tc_pack_split8(acc, hi, lo);
-          }
-          const uint32_t soff = (uint32_t)r * 128u + (uint32_t)((sub ^ (r & 7)) << 4);
-          st_shared_v4(sA_hi + soff, hi); st_shared_v4(sA_lo + soff, lo);
-        }
+        const uint32_t off = (uint32_t)r * 128u + (uint32_t)((sub ^ (r & 7)) << 4);
+        st_shared_v4(sA + off, hi); st_shared_v4(sA + (uint32_t)(TC_BM * 128) + off, lo);
       }
       if (stampit) pstamp[4 * pj + 2] = clock64();
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA (async proxy)
@@ -967,6 +946,7 @@ __global__ void __launch_bounds__(DIRECT ? TC_THREADS_DIRECT : TC_THREADS, 1) k_
   constexpr uint32_t IDESC2 = umma_idesc_bf16(TC_BM, 2 * BN);
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_full[NS], bar_empty[NS], bar_acc;
+  __shared__ __align__(8) uint64_t bar_raw[DIRECT ? NS : 1];   // direct mode: the raw fp32 A tile of a stage has landed
   __shared__ uint32_t tmem_base_s;
   __shared__ long long s_stamp[8];
   __shared__ long long s_pstamp[DIRECT ? 16 : 1];  // diagnostics: producer-phase stamps of the first iterations
@@ -998,10 +978,11 @@ __global__ void __launch_bounds__(DIRECT ? TC_THREADS_DIRECT : TC_THREADS, 1) k_
   if (threadIdx.x == 0) {
     // full barrier: the TMA thread's expect_tx arrival (+ one arrival per producer warp of the owning group when DIRECT)
     for (int s = 0; s < NS; ++s) { mbar_init(&bar_full[s], DIRECT ? 5 : 1); mbar_init(&bar_empty[s], 1); }
+    if (DIRECT) for (int s = 0; s < NS; ++s) mbar_init(&bar_raw[s], 1);
     mbar_init(&bar_acc, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    if (!DIRECT) { prefetch_tmap(&P.tmA_hi[0]); prefetch_tmap(&P.tmA_lo[0]); }
+    prefetch_tmap(&P.tmA_hi[0]); if (!DIRECT) prefetch_tmap(&P.tmA_lo[0]);
     prefetch_tmap(&P.tmW_hi); prefetch_tmap(&P.tmW_lo);
   }
   if (warp == 1) {   // TMEM: BN fp32 accumulator columns x 128 lanes
@@ -1078,7 +1059,21 @@ __global__ void __launch_bounds__(DIRECT ? TC_THREADS_DIRECT : TC_THREADS, 1) k_
           load_W(it, stage);
         }
         if (dbg && it == it1 - 1) s_stamp[2] = clock64();          // last stage request issued
-        if constexpr (!DIRECT) load_A(it, stage);
+        if constexpr (!DIRECT) {
+          load_A(it, stage);
+        } else {
+          // raw fp32 tile of the source that holds this 64-channel chunk (channel concat = two tensors, two map sets)
+          const uint32_t rb = smem_u32(&bar_raw[stage]);
+          mbar_expect_tx(&bar_raw[stage], (uint32_t)(TC_BM * 256));
+          const bool seg1 = it >= it_main;
+          const DirectSeg& S = P.dseg[seg1 ? 1 : 0];
+          const int tap = seg1 ? 0 : it / kch;
+          const int c0 = seg1 ? (it - it_main) * TC_BK : (it - tap * kch) * TC_BK;
+          const CUtensorMap* m0 = seg1 ? P.tmA2_hi : P.tmA_hi;
+          const CUtensorMap* m1 = seg1 ? P.tmA2_lo : P.tmA_lo;
+          if (c0 < S.C0) tc_load_A32(g, T, m0, seg1 ? 1 : P.taps, tap, c0, smem0 + stage * STAGE, rb);
+          else           tc_load_A32(g, T, m1, seg1 ? 1 : P.taps, tap, c0 - S.C0, smem0 + stage * STAGE, rb);
+        }
         if (++stage == NS) { stage = 0; phase ^= 1u; }
       }
     }
@@ -1115,7 +1110,7 @@ __global__ void __launch_bounds__(DIRECT ? TC_THREADS_DIRECT : TC_THREADS, 1) k_
   } else {
     if constexpr (DIRECT) {
       const int pw = warp - 2;                    // producer warp 0..7: group = pw >> 2
-      tc_produce_A<BN>(P, g, T, it0, it1, it_main, kch, smem0, bar_full, bar_empty, tbl, s_rowinfo, pw >> 2, (pw & 3) * 32 + lane, dbg ? s_pstamp : nullptr);
+      tc_produce_A<BN>(P, g, T, it0, it1, it_main, kch, smem0, bar_raw, bar_full, tbl, s_rowinfo, pw >> 2, (pw & 3) * 32 + lane, dbg ? s_pstamp : nullptr);
     }
     if (!DIRECT || warp < 6) {
       tc_epilogue<BN, EPI, true>(P, g, T, n0, (int)blockIdx.z, tmem_base, s_bias, &bar_acc, 0u, dbg ? s_stamp : nullptr);
@@ -1156,14 +1151,10 @@ __global__ void __launch_bounds__(DIRECT ? TC_THREADS_DIRECT : TC_THREADS, 1) k_
 // split-K epilogue for the tensor-core path (fixed summation order).  A CTA owns 32 rows x 32
 // channels: warp w = channel quad, lane = row, so the per-channel statistics reduce with three
 // shuffles over aligned 8-row groups (never straddling a (sample, plane) boundary).
-__device__ __forceinline__ void tc_splitk_unit(const TcConvParams& P, int mblk, int nblk) {
-  const Geo g = P.geo;
+// sum of the split-K partial tiles (fixed order) + bias + residual for 4 channels of one output row
+__device__ __forceinline__ float4 tc_splitk_sum(const TcConvParams& P, const Geo& g, size_t m, int n, int b, int p, int y, int x,
+                                                const float4& bv0) {
   const size_t M = (size_t)P.B * g.L;
-  const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
-  const size_t m = (size_t)mblk * 32 + lane;
-  const int n = nblk * 32 + wq * 4;
-  float4 bv0 = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (P.bias) bv0 = __ldg(reinterpret_cast<const float4*>(P.bias + n));     // cold line: issue first
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
   const float* pp = P.partial + m * P.Cout + n;
   const size_t zstride = M * P.Cout;
@@ -1180,9 +1171,6 @@ __device__ __forceinline__ void tc_splitk_unit(const TcConvParams& P, int mblk, 
     s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
   }
   s.x += bv0.x; s.y += bv0.y; s.z += bv0.z; s.w += bv0.w;
-  const int b = (int)(m / g.L), tok = (int)(m - (size_t)b * g.L);
-  int p = 0, y = 0, x = 0;
-  tc_decode_tok(g, tok, p, y, x);
   if (P.resid) {
     if (P.resid_mode == RS_NONE) {
       const float4 rv = __ldg(reinterpret_cast<const float4*>(P.resid + m * P.Cout + n));
@@ -1204,6 +1192,20 @@ __device__ __forceinline__ void tc_splitk_unit(const TcConvParams& P, int mblk, 
       s.z += 0.25f * (r0.z + r1.z + r2.z + r3.z); s.w += 0.25f * (r0.w + r1.w + r2.w + r3.w);
     }
   }
+  return s;
+}
+
+__device__ __forceinline__ void tc_splitk_unit(const TcConvParams& P, int mblk, int nblk) {
+  const Geo g = P.geo;
+  const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
+  const size_t m = (size_t)mblk * 32 + lane;
+  const int n = nblk * 32 + wq * 4;
+  float4 bv0 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (P.bias) bv0 = __ldg(reinterpret_cast<const float4*>(P.bias + n));     // cold line: issue first
+  const int b = (int)(m / g.L), tok = (int)(m - (size_t)b * g.L);
+  int p = 0, y = 0, x = 0;
+  tc_decode_tok(g, tok, p, y, x);
+  const float4 s = tc_splitk_sum(P, g, m, n, b, p, y, x, bv0);
   *reinterpret_cast<float4*>(P.out + m * P.Cout + n) = s;
   if (P.csum) {
     float v[4] = {s.x, s.y, s.z, s.w}, q[4] = {s.x * s.x, s.y * s.y, s.z * s.z, s.w * s.w};
@@ -1215,6 +1217,120 @@ __device__ __forceinline__ void tc_splitk_unit(const TcConvParams& P, int mblk, 
       double* dst = P.csum + (((size_t)b * 3 + p) * P.Cout + n) * 2;
 #pragma unroll
       for (int i = 0; i < 4; ++i) { atomicAdd(dst + 2 * i, (double)v[i]); atomicAdd(dst + 2 * i + 1, (double)q[i]); }
+    }
+  }
+}
+
+// Split-K reduction FUSED with the consumer's GroupNorm + apply, for levels where one sample has <= 128 tokens: a CTA owns
+// every token of sample b for CU channels (whole GroupNorm groups), so the statistics of the reduced tensor are CTA-local
+// and the next op's operand  y = silu?(GN(x) [FiLM])  -> split bf16  can be written in the same pass — no channel-sum
+// atomics, no stand-alone apply launch.  Still writes the fp32 tensor (residual / skip consumers) and its per-channel sums.
+// Thread t: channel quad t % (CU/4), rows t / (CU/4) + k * (256 / (CU/4)).
+template <int CU>
+__global__ void __launch_bounds__(256) k_tc_splitk_reduce_apply(const __grid_constant__ TcConvParams P) {
+  constexpr int QL = CU / 4;                 // float4 lanes per row
+  constexpr int RPP = 256 / QL;              // rows per pass (64 or 32)
+  constexpr int RPW = 32 / QL;               // rows per warp and pass (8 or 4): never straddles a plane
+  constexpr int MAXPASS = 128 / RPP;
+  MTV_PDL_TRIGGER();
+  mtv_prefetch_slice(P.fa.pf0, P.fa.pf1, P.fa.pf_bytes, blockIdx.x + gridDim.x * blockIdx.y, gridDim.x * gridDim.y);
+  const Geo g = P.geo;
+  const int L = g.L, C = P.Cout;
+  const int b = blockIdx.y, n = blockIdx.x * CU + (threadIdx.x % QL) * 4;
+  const int r0 = threadIdx.x / QL, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int npass = (L + RPP - 1) / RPP;
+  __shared__ float s_part[128 / RPW][CU][2];       // per aligned row group: channel sums, sums of squares
+  __shared__ float s_a[3][CU], s_d[3][CU];
+  // static per-channel parameters do not depend on the producer: fetch before the dependency resolves
+  float4 bv0 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (P.bias) bv0 = __ldg(reinterpret_cast<const float4*>(P.bias + n));
+  float pg = 0.f, pb = 0.f, psc = 0.f, psh = 0.f;
+  if (threadIdx.x < CU) {
+    const int c = blockIdx.x * CU + threadIdx.x;
+    pg = __ldg(P.fa.gamma + c); pb = __ldg(P.fa.beta + c);
+  }
+  MTV_PDL_WAIT();
+  if (threadIdx.x < CU && P.fa.film) {
+    const int c = blockIdx.x * CU + threadIdx.x;
+    const float* f = P.fa.film + (size_t)b * P.fa.film_stride;
+    psc = __ldg(f + c); psh = __ldg(f + C + c);
+  }
+  float4 val[MAXPASS];
+#pragma unroll
+  for (int k = 0; k < MAXPASS; ++k) {
+    const int r = r0 + k * RPP;
+    if (k < npass && r < L) {
+      int p, y, x; tc_decode_tok(g, r, p, y, x);
+      const size_t m = (size_t)b * L + r;
+      const float4 s = tc_splitk_sum(P, g, m, n, b, p, y, x, bv0);
+      *reinterpret_cast<float4*>(P.out + m * C + n) = s;
+      val[k] = s;
+      float v[4] = {s.x, s.y, s.z, s.w}, q[4] = {s.x * s.x, s.y * s.y, s.z * s.z, s.w * s.w};
+#pragma unroll
+      for (int off = QL; off < 32; off <<= 1)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { v[i] += __shfl_xor_sync(0xffffffffu, v[i], off); q[i] += __shfl_xor_sync(0xffffffffu, q[i], off); }
+      if (lane < QL) {
+        const int grp = (k * RPP) / RPW + warp;      // aligned row group index = first row / RPW
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { s_part[grp][lane * 4 + i][0] = v[i]; s_part[grp][lane * 4 + i][1] = q[i]; }
+      }
+    }
+  }
+  __syncthreads();
+  // per (plane, channel) sums in fixed order -> csum (complete: plain stores) -> group statistics -> affine (a, d)
+  const int nxy = g.res * g.res, npl = g.t * g.res;
+  __shared__ double s_cs[3][CU][2];
+  if (threadIdx.x < 3 * CU) {
+    const int p = threadIdx.x / CU, c = threadIdx.x - p * CU;
+    const int g0 = (p == 0 ? 0 : nxy + (p - 1) * npl) / RPW, g1 = (p == 0 ? nxy : nxy + p * npl) / RPW;
+    double sm = 0.0, sq = 0.0;
+    for (int gi = g0; gi < g1; ++gi) { sm += (double)s_part[gi][c][0]; sq += (double)s_part[gi][c][1]; }
+    s_cs[p][c][0] = sm; s_cs[p][c][1] = sq;
+    if (P.csum) {
+      double* dst = P.csum + (((size_t)b * 3 + p) * C + blockIdx.x * CU + c) * 2;
+      dst[0] = sm; dst[1] = sq;
+    }
+  }
+  __syncthreads();
+  __shared__ double s_st[3][CU][2];                // (rstd, mean) of the group of channel c in plane p
+  if (threadIdx.x < 3 * CU) {
+    const int p = threadIdx.x / CU, c = threadIdx.x - p * CU;
+    const int cpg = C / 32;
+    const int cg0 = (c / cpg) * cpg;               // CU is a multiple of the group width: the group lies inside this CTA
+    double sm = 0.0, sq = 0.0;
+    for (int ci = 0; ci < cpg; ++ci) {
+      if (P.fa.joint) { for (int pp = 0; pp < 3; ++pp) { sm += s_cs[pp][cg0 + ci][0]; sq += s_cs[pp][cg0 + ci][1]; } }
+      else { sm += s_cs[p][cg0 + ci][0]; sq += s_cs[p][cg0 + ci][1]; }
+    }
+    const double cnt = (double)cpg * (P.fa.joint ? (double)L : (double)(p == 0 ? nxy : npl));
+    const double mean = sm / cnt;
+    double var = sq / cnt - mean * mean; var = var < 0.0 ? 0.0 : var;
+    s_st[p][c][0] = rsqrt(var + 1e-5); s_st[p][c][1] = mean;
+  }
+  __syncthreads();
+  if (threadIdx.x < CU) {                          // gamma / beta / FiLM of channel c live in thread c's registers
+    const int c = threadIdx.x;
+#pragma unroll
+    for (int p = 0; p < 3; ++p) {
+      double a = s_st[p][c][0] * (double)pg;
+      double d = (double)pb - s_st[p][c][1] * a;
+      if (P.fa.film) { const double sc = 1.0 + (double)psc; a *= sc; d = d * sc + (double)psh; }
+      s_a[p][c] = (float)a; s_d[p][c] = (float)d;
+    }
+  }
+  __syncthreads();
+  const int cl = (threadIdx.x % QL) * 4;
+#pragma unroll
+  for (int k = 0; k < MAXPASS; ++k) {
+    const int r = r0 + k * RPP;
+    if (k < npass && r < L) {
+      const int p = r < nxy ? 0 : (r < nxy + npl ? 1 : 2);
+      const float4 na = *reinterpret_cast<const float4*>(&s_a[p][cl]), nd = *reinterpret_cast<const float4*>(&s_d[p][cl]);
+      float4 v = val[k];
+      v.x = fmaf(v.x, na.x, nd.x); v.y = fmaf(v.y, na.y, nd.y); v.z = fmaf(v.z, na.z, nd.z); v.w = fmaf(v.w, na.w, nd.w);
+      if (P.fa.silu) { v.x = silu_tc(v.x); v.y = silu_tc(v.y); v.z = silu_tc(v.z); v.w = silu_tc(v.w); }
+      tc_store_split(v, P.fa.hi, P.fa.lo, ((size_t)b * L + r) * C + n);
     }
   }
 }
@@ -1582,7 +1698,14 @@ cudaError_t launch_conv_tc(const TcConvParams& P, cudaStream_t s) {
 #undef MTV_TC_LAUNCH
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  if (P.ksplit > 1) {
+  if (P.ksplit > 1 && P.fa.hi) {
+    const int cu = (P.Cout / 32) > 16 ? 32 : 16;     // whole GroupNorm groups per CTA (host checked divisibility)
+    dim3 rgrid(P.Cout / cu, P.B);
+    cudaError_t le_ = cu == 16 ? launch_kc(PDL_CLASS_REDUCE, k_tc_splitk_reduce_apply<16>, rgrid, dim3(256), (size_t)0, s, P)
+                               : launch_kc(PDL_CLASS_REDUCE, k_tc_splitk_reduce_apply<32>, rgrid, dim3(256), (size_t)0, s, P);
+    if (le_ != cudaSuccess) return le_;
+    e = cudaGetLastError();
+  } else if (P.ksplit > 1) {
     dim3 rgrid(M / 32, P.Cout / 32);
     { cudaError_t le_ = launch_kc(PDL_CLASS_REDUCE, k_tc_splitk_epilogue, dim3(rgrid), dim3(256), (size_t)(0), s, P); if (le_ != cudaSuccess) return le_; }
     e = cudaGetLastError();

@@ -119,7 +119,12 @@ struct Weight {
   void* hi = nullptr; void* lo = nullptr;   // split-bf16 K-major copy [taps][Cout][Cin] for the tcgen05 path
 };
 
-struct Tensor { float* p = nullptr; int C = 0; int level = 0; double* csum = nullptr; /* [B][3][C][2] per-channel sums, or null */ };
+struct Tensor {
+  float* p = nullptr; int C = 0; int level = 0; double* csum = nullptr; /* [B][3][C][2] per-channel sums, or null */
+  // set when a split-K tensor-core conv at a small level produced this tensor: its reduction kernel can also write the
+  // first simple consumer's normalised operand (FusedApply)
+  std::shared_ptr<mtv::TcConvParams> prod;
+};
 
 struct RunCtx {
   const float* x = nullptr; const float* cond = nullptr; const float* image_cond = nullptr;
@@ -165,8 +170,9 @@ struct MtvHandle_t {
   int64_t weight_bytes = 0;
   // feature bits (MTV_TC_MASK): 0-4 op classes on the tensor-core kernel, 5 split-K, 6 tcgen05 attention, 7 small levels,
   // 8 fused GroupNorm statistics, 9 launch fusions, 10 weight L2 prefetch, 11 L2-persisting small-tensor arena;
+  // 14 consumer GroupNorm + apply fused into small-level split-K reductions;
   // opt-in (measured slower on B200, kept for A/B — profiles/r01_s2_*.md): 12 persistent chain kernel, 13 direct A operand
-  int tc_mask = 0xfff;
+  int tc_mask = 0x4fff;
   cudaStream_t cap_stream = nullptr;
   cudaStream_t capture_stream() {
     if (!cap_stream) CK(cudaStreamCreateWithFlags(&cap_stream, cudaStreamNonBlocking));
@@ -314,13 +320,14 @@ EncodeTiledFn encode_tiled_fn() {
 }
 // bf16 tensor, innermost dimension contiguous, 128-byte swizzle, zero fill out of bounds
 CUtensorMap make_tmap_bf16(void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
-                           int swizzle_bytes = 128) {
+                           int swizzle_bytes = 128, bool f32 = false) {
   CUtensorMap m;
   cuuint64_t gd[5]; cuuint64_t gs[4]; cuuint32_t bx[5]; cuuint32_t es[5];
   for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
   for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
-  CUresult r = encode_tiled_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, base, gd, gs, bx, es,
-                                 CU_TENSOR_MAP_INTERLEAVE_NONE,
+  CUresult r = encode_tiled_fn()(&m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, base, gd, gs,
+                                 bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                 swizzle_bytes == 0 ? CU_TENSOR_MAP_SWIZZLE_NONE :
                                  swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                                                       : (swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B),
                                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -437,6 +444,22 @@ struct Builder {
     const int C = S.C0 + S.C1;
     const size_t bytes = (size_t)B * g.L * C * 2;
     SplitBuf out; out.hi = dalloc(bytes); out.lo = dalloc(bytes);
+    // a simple consumer (one source, same geometry, fused statistics) of a small-level split-K conv: the producer's reduction
+    // kernel writes this operand itself (k_tc_splitk_reduce_apply) — no apply launch
+    if (norm_id >= 0 && !raw_out && S.C1 == 0 && S.resample == RS_NONE) {
+      const NormSpec& n = norms[norm_id];
+      TcConvParams* pr = n.x0.prod.get();
+      if (pr && !n.has_x1 && n.x0.p == S.src0 && n.x0.C == C && pr->out == S.src0 && !pr->fa.hi && fuse_gn()) {
+        FusedApply& F = pr->fa;
+        F.gamma = n.gamma; F.beta = n.beta; F.joint = n.joint ? 1 : 0; F.silu = S.silu; F.hi = out.hi; F.lo = out.lo;
+        if (n.film_off >= 0) { F.film = film_buf + n.film_off; F.film_stride = h->arch.J; }
+        if (consumer_w && ((h->tc_mask >> 10) & 1)) {
+          auto it = h->tc_w.find(consumer_w);
+          if (it != h->tc_w.end()) { F.pf0 = it->second.first; F.pf1 = it->second.second; F.pf_bytes = (unsigned long long)S.taps * C * consumer_cout * 2; }
+        }
+        return out;
+      }
+    }
     ApplyParams A{};
     A.src0 = S.src0; A.src1 = S.src1; A.C0 = S.C0; A.C1 = S.C1;
     A.silu = S.silu; A.resample = S.resample; A.B = B; A.geo = g; A.hi = out.hi; A.lo = out.lo;
@@ -472,21 +495,31 @@ struct Builder {
     return out;
   }
   void make_A_maps(const SplitBuf& buf, int C, int taps, const Geo& g, CUtensorMap* a_hi, CUtensorMap* a_lo) {
-    void* ptr[2] = {buf.hi, buf.lo}; CUtensorMap* dst[2] = {a_hi, a_lo};
+    void* ptr[2] = {buf.hi, buf.lo};
+    make_A_maps_n(ptr, 2, C, taps, g, a_hi, a_lo, false);
+  }
+  // fp32 maps of ONE raw activation tensor (direct mode): unswizzled 256-byte rows
+  void make_A_maps_f32(const float* src, int C, int taps, const Geo& g, CUtensorMap* dst2) {
+    void* ptr[2] = {(void*)src, nullptr};
+    make_A_maps_n(ptr, 1, C, taps, g, dst2, nullptr, true);
+  }
+  void make_A_maps_n(void* const* ptr, int n, int C, int taps, const Geo& g, CUtensorMap* a_hi, CUtensorMap* a_lo, bool f32) {
+    CUtensorMap* dst[2] = {a_hi, a_lo};
     const bool small = g.L <= 128;
     const uint32_t spt = small ? (uint32_t)(128 / g.L) : 1u;          // samples per tile (kernels_tc.cu: tc_tile)
-    const uint64_t rowb = (uint64_t)C * 2;
-    for (int k = 0; k < 2; ++k) {
+    const uint64_t rowb = (uint64_t)C * (f32 ? 4 : 2);
+    const int sw = f32 ? 0 : 128;
+    for (int k = 0; k < n; ++k) {
       char* base = (char*)ptr[k];
       if (taps == 1 && !small) {
         const uint64_t dims[2] = {(uint64_t)C, (uint64_t)B * g.L}; const uint64_t str[1] = {rowb};
         const uint32_t box[2] = {64, 128};
-        dst[k][0] = make_tmap_bf16(base, 2, dims, str, box);
+        dst[k][0] = make_tmap_bf16(base, 2, dims, str, box, sw, f32);
       } else if (taps == 1) {
         const uint64_t dims[3] = {(uint64_t)C, (uint64_t)g.L, (uint64_t)B}; const uint64_t str[2] = {rowb, rowb * g.L};
         const uint32_t box0[3] = {64, (uint32_t)(g.res * g.res), spt}, box1[3] = {64, (uint32_t)(g.t * g.res), spt};
-        dst[k][0] = make_tmap_bf16(base, 3, dims, str, box0);
-        dst[k][1] = make_tmap_bf16(base, 3, dims, str, box1);
+        dst[k][0] = make_tmap_bf16(base, 3, dims, str, box0, sw, f32);
+        dst[k][1] = make_tmap_bf16(base, 3, dims, str, box1, sw, f32);
       } else {
         const uint32_t hb_xy = small ? (uint32_t)g.res : (uint32_t)(128 / g.res);
         const uint32_t hb_pl = small ? (uint32_t)g.t : (uint32_t)(128 / g.res);
@@ -494,13 +527,13 @@ struct Builder {
           const uint64_t dims[4] = {(uint64_t)C, (uint64_t)g.res, (uint64_t)g.res, (uint64_t)B};
           const uint64_t str[3] = {rowb, rowb * g.res, rowb * g.L};
           const uint32_t box[4] = {64, (uint32_t)g.res, hb_xy, spt};
-          dst[k][0] = make_tmap_bf16(base, 4, dims, str, box);
+          dst[k][0] = make_tmap_bf16(base, 4, dims, str, box, sw, f32);
         }
         {
           const uint64_t dims[5] = {(uint64_t)C, (uint64_t)g.res, (uint64_t)g.t, 2, (uint64_t)B};
           const uint64_t str[4] = {rowb, rowb * g.res, rowb * g.res * g.t, rowb * g.L};
           const uint32_t box[5] = {64, (uint32_t)g.res, hb_pl, 1, spt};
-          dst[k][1] = make_tmap_bf16(base + rowb * g.res * g.res, 5, dims, str, box);
+          dst[k][1] = make_tmap_bf16(base + rowb * g.res * g.res, 5, dims, str, box, sw, f32);
         }
       }
     }
@@ -509,7 +542,7 @@ struct Builder {
   // concat themselves, so neither the apply launch nor the split-bf16 copy of the activation exists.
   bool use_direct() const { return h->cfg.kernel_path != 1 && ((h->tc_mask >> 13) & 1); }
   bool direct_seg_ok(const KSeg& S, int norm_id, const Geo& g) const {
-    if (S.C0 % 64 || S.C1 % 64) return false;
+    if (S.C0 % 64 || S.C1 % 64 || S.resample != RS_NONE) return false;     // resampled sources keep the apply pass
     if (norm_id < 0) return true;
     const NormSpec& n = norms[norm_id];
     const bool small = g.L <= 128;
@@ -555,6 +588,8 @@ struct Builder {
     if (direct) {
       T.direct = 1;
       T.dseg[0] = make_direct_seg(S, norm0);
+      make_A_maps_f32(S.src0, S.C0, S.taps, P.geo, T.tmA_hi);
+      if (S.C1) make_A_maps_f32(S.src1, S.C1, S.taps, P.geo, T.tmA_lo);
     } else {
       const SplitBuf a0 = o.pre0 ? *o.pre0 : emit_apply(name, S, P.geo, norm0, o.raw_out, S.w, P.Cout);
       make_A_maps(a0, T.Cin, S.taps, P.geo, T.tmA_hi, T.tmA_lo);
@@ -574,6 +609,8 @@ struct Builder {
       T.Cin2 = X.C0 + X.C1;
       if (direct) {
         T.dseg[1] = make_direct_seg(X, -1);
+        make_A_maps_f32(X.src0, X.C0, 1, P.geo, T.tmA2_hi);
+        if (X.C1) make_A_maps_f32(X.src1, X.C1, 1, P.geo, T.tmA2_lo);
       } else {
         const SplitBuf a1 = o.pre1 ? *o.pre1 : emit_apply(name + ".skip", X, P.geo, norm1, nullptr);
         make_A_maps(a1, T.Cin2, 1, P.geo, T.tmA2_hi, T.tmA2_lo);
@@ -600,6 +637,11 @@ struct Builder {
     op.fn = [tp](cudaStream_t s) { return launch_conv_tc(*tp, s); };
     op.tc = tp;
     tc_wptr[tp.get()] = h->tc_w.at(S.w);
+    {
+      const int cpg = P.Cout / 32;
+      const bool groups_fit = (cpg <= 16 && 16 % cpg == 0) || cpg == 32;
+      if (out_t && ks > 1 && P.geo.L <= 128 && !o.qkv && T.csum && groups_fit && ((h->tc_mask >> 14) & 1)) out_t->prod = tp;
+    }
     if (!direct) op.ctype = CH_GEMM;
     pl->ops.push_back(op);
   }
@@ -632,7 +674,7 @@ struct Builder {
     size_t i = 0;
     while (i < pl->ops.size()) {
       size_t j = i;
-      while (j < pl->ops.size() && pl->ops[j].phase == 1 && pl->ops[j].ctype >= 0) ++j;
+      while (j < pl->ops.size() && pl->ops[j].phase == 1 && pl->ops[j].ctype >= 0 && !(pl->ops[j].tc && pl->ops[j].tc->fa.hi)) ++j;
       std::vector<ChainOp> sub;
       for (size_t k = i; k < j; ++k) {
         const Op& o = pl->ops[k];

@@ -52,6 +52,15 @@ struct DirectSeg {
   int mode;                                               // DS_*
 };
 
+// Consumer GroupNorm + apply fused into the producer's split-K reduction (k_tc_splitk_reduce_apply): the next op's
+// operand  y = silu?(GN(out) [FiLM]) -> split bf16  is written by the reduction itself.  hi == nullptr: not fused.
+struct FusedApply {
+  const float* gamma; const float* beta; const float* film; int film_stride;
+  int joint; int silu;
+  void* hi; void* lo;                                  // __nv_bfloat16 [B][L][Cout]
+  const void* pf0; const void* pf1; unsigned long long pf_bytes;   // L2 prefetch of the consumer GEMM's weights
+};
+
 // D[B*L][Cout] = sum_tap A_tap[B*L][Cin] * W[tap][Cout][Cin]^T   (+bias, +residual)
 struct TcConvParams {
   // L > 128 : taps==9: [0] xy plane (C,W,H,B), [1] yt|xt planes (C,W,H,2,B), 128-token boxes; taps==1: [0] = (C, B*L)
@@ -76,6 +85,7 @@ struct TcConvParams {
   int direct; DirectSeg dseg[2];
   // L2 prefetch of the NEXT tap-GEMM's (HBM-cold) split weights, issued at kernel entry (one slice per CTA)
   const void* pf0; const void* pf1; unsigned long long pf_bytes;
+  FusedApply fa;
 };
 constexpr int TC_TABLE_ENTRIES = 3072;   // direct mode: (a, d) pairs per CTA = (sample-plane pairs of the tile) x channels
 
