@@ -13,7 +13,8 @@ value     chunk-steps/s over all ranks, inputs resident in HBM, CUDA-event timed
           max over ranks; weak scaling (each rank samples its own chunks, one
           all-gather of the final latents inside the timed region when N>1).
 e2e       same metric through the public nn.Module API with HOST (pinned) buffers:
-          every step copies x/cond/image_cond/t host->device and eps device->host.
+          every step copies x/cond/image_cond/t host->device, runs the UNet forward and
+          the DDIM update, and reads the updated latent back device->host (sync per step).
 roofline  dominant kernel family of one forward, CUDA events around each launch.
 cpu_baseline / --impl reference
           the CPU restatement of the reference path (oracle/unet_oracle.py; the
@@ -258,12 +259,17 @@ def main():
         x_d, c_d, ic_d, t_d = torch.empty_like(img), torch.empty_like(cond), torch.empty_like(ic), torch.empty((B,), device=dev, dtype=torch.long)
 
         def e2e_step(i):
-            t_h.fill_(pairs[i % (len(pairs) - 1)][0])
+            time_, tn = pairs[i % (len(pairs) - 1)]
+            t_h.fill_(time_)
             x_d.copy_(x_h, non_blocking=True); c_d.copy_(cond_h, non_blocking=True)
             ic_d.copy_(ic_h, non_blocking=True); t_d.copy_(t_h, non_blocking=True)
             eps = model(x_d, c_d, ic_d, t_d)
-            eps_h.copy_(eps, non_blocking=True)
-            stream.synchronize()                          # the caller reads eps on the host
+            noise = torch.randn_like(x_d)
+            sr, srm1, san, c, sigma = ddpm.step_scalars(time_, tn)
+            _lib.check(lib.mtv_ddim_step(h, x_d.data_ptr(), eps.data_ptr(), noise.data_ptr(), x_d.numel(), sr, srm1, san, c,
+                                         sigma, 0, stream.cuda_stream), "mtv_ddim_step")
+            eps_h.copy_(x_d, non_blocking=True)           # the step's result: the updated latent x_{t-1}
+            stream.synchronize()                          # the caller reads it on the host
 
         for i in range(3):
             e2e_step(i)
@@ -325,6 +331,16 @@ def main():
         roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
                 "frac": ach / pk["hbm_gbs"], "traffic": None, "peak_source": f"{pk['source']} (MEASURED_PEAKS.json hbm_gbs)"}
     roof["us_per_forward"] = d["us_per_forward"]
+    roof["launches_per_forward"] = d["launch_groups"]
+    # DRAM traffic of the same kernel family from the committed ncu capture (profiles/r01_traffic.json, written by
+    # scripts/summarize_traffic.py from `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum`); per launch like `achieved`
+    tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tp):
+        tr = json.load(open(tp)).get(f"B{B}", {}).get(dom)
+        if tr:
+            roof["traffic"] = tr["dram_bytes"] / max(1, tr["launches"])
+            roof["traffic_per_forward"] = tr["dram_bytes"]
+            roof["algorithmic_bytes_per_forward"] = d["mbytes"] * 1e6
     # whole-step HBM view (0.54 GB algorithmic bytes per step at B=1)
     step_bytes = info["weight_bytes"] + B * (10.6e6 + 0.14e6)
     roof["step_hbm_frac"] = (step_bytes / ((ms_total / K) * 1e-3)) / 1e9 / pk["hbm_gbs"]
@@ -346,7 +362,7 @@ def main():
         },
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": e2e_ms / K, "api": "DiffusionWrapper.forward with pinned host buffers, sync per step"},
+                "ms_per_step": e2e_ms / K, "api": "DiffusionWrapper.forward + DDIM update, pinned host buffers in, updated latent out, sync per step"},
         "gpu_launches": int(K * (info["launches"] + 1)),
         "roofline": roof,
         "kernel_families_us": {k: round(v["us_per_forward"], 1) for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["us_per_forward"])},

@@ -74,6 +74,14 @@ __device__ __forceinline__ void a_mma(uint32_t tmem_d, uint64_t adesc, uint64_t 
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
 }
+// one lane of a converged warp: the TMA / MMA warps run their loops in all lanes (uniform control flow, descriptors in
+// uniform registers) and elect only around the issuing instructions — inside an `if (lane == 0)` region ptxas wraps every
+// tcgen05.mma in an ELECT / R2UR.BROADCAST waterfall (~115 cycles per MMA; see kernels_tc.cu: elect_one)
+__device__ __forceinline__ bool a_elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void a_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(a_smem_u32(bar)) : "memory");
 }
@@ -223,22 +231,28 @@ __global__ void __launch_bounds__(AT_THREADS, (D <= 32) ? 2 : 1) k_attn_tc(const
 
   if (warp == 0) {
     // =============================== TMA producer ===============================
-    if (lane == 0) {
-      a_mbar_expect_tx(&bar_q, 2 * SM::Q_BYTES);
-      a_tma_2d(sQ_hi, &P.tmQ_hi, a_smem_u32(&bar_q), 0, bh * P.L + t_lo + q0);
-      a_tma_2d(sQ_lo, &P.tmQ_lo, a_smem_u32(&bar_q), 0, bh * P.L + t_lo + q0);
+    {
+      if (a_elect_one()) {
+        a_mbar_expect_tx(&bar_q, 2 * SM::Q_BYTES);
+        a_tma_2d(sQ_hi, &P.tmQ_hi, a_smem_u32(&bar_q), 0, bh * P.L + t_lo + q0);
+        a_tma_2d(sQ_lo, &P.tmQ_lo, a_smem_u32(&bar_q), 0, bh * P.L + t_lo + q0);
+      }
+      __syncwarp();
       int stage = 0; uint32_t phase = 0;
       for (int j = 0; j < nblk; ++j) {
         a_mbar_wait(&bar_empty[stage], phase ^ 1u);
-        a_mbar_expect_tx(&bar_full[stage], SM::STAGE_TX);
-        const uint32_t sK_hi = sStage0 + stage * SM::STAGE, sK_lo = sK_hi + SM::K_SLOT;
-        const uint32_t sV_hi = sK_lo + SM::K_SLOT, sV_lo = sV_hi + SM::V_SLOT;
-        const uint32_t fb = a_smem_u32(&bar_full[stage]);
-        const int krow = bh * P.L + t_lo + j * AT_BKV;
-        a_tma_2d(sK_hi, &P.tmK_hi, fb, 0, krow);
-        a_tma_2d(sK_lo, &P.tmK_lo, fb, 0, krow);
-        a_tma_2d(sV_hi, &P.tmV_hi, fb, t_lo + j * AT_BKV, bh * D);
-        a_tma_2d(sV_lo, &P.tmV_lo, fb, t_lo + j * AT_BKV, bh * D);
+        if (a_elect_one()) {
+          a_mbar_expect_tx(&bar_full[stage], SM::STAGE_TX);
+          const uint32_t sK_hi = sStage0 + stage * SM::STAGE, sK_lo = sK_hi + SM::K_SLOT;
+          const uint32_t sV_hi = sK_lo + SM::K_SLOT, sV_lo = sV_hi + SM::V_SLOT;
+          const uint32_t fb = a_smem_u32(&bar_full[stage]);
+          const int krow = bh * P.L + t_lo + j * AT_BKV;
+          a_tma_2d(sK_hi, &P.tmK_hi, fb, 0, krow);
+          a_tma_2d(sK_lo, &P.tmK_lo, fb, 0, krow);
+          a_tma_2d(sV_hi, &P.tmV_hi, fb, t_lo + j * AT_BKV, bh * D);
+          a_tma_2d(sV_lo, &P.tmV_lo, fb, t_lo + j * AT_BKV, bh * D);
+        }
+        __syncwarp();
         if (++stage == AT_NS) { stage = 0; phase ^= 1u; }
       }
     }
@@ -246,18 +260,24 @@ __global__ void __launch_bounds__(AT_THREADS, (D <= 32) ? 2 : 1) k_attn_tc(const
     MTV_PDL_TRIGGER();
   } else if (warp == 1) {
     // =============================== MMA issuer =================================
-    if (lane == 0) {
+    // whole warp in the loop, one elected lane issues; descriptors = base descriptor + (byte offset >> 4)
+    {
+      const uint64_t dQK = a_desc(smem0, SM::ROWB);          // Q / K tiles: swizzle span = row bytes
+      const uint64_t dPV = a_desc(smem0, 128);               // P / V^T tiles: 128-byte rows
+      auto off16 = [&](uint32_t addr) { return (uint64_t)((addr - smem0) >> 4); };
       auto issue_S = [&](int stage) {
         const uint32_t sK_hi = sStage0 + stage * SM::STAGE, sK_lo = sK_hi + SM::K_SLOT;
+        const uint64_t qh0 = dQK + off16(sQ_hi), ql0 = dQK + off16(sQ_lo), kh0 = dQK + off16(sK_hi), kl0 = dQK + off16(sK_lo);
+        if (a_elect_one()) {
 #pragma unroll
-        for (int k = 0; k < D / 16; ++k) {
-          const uint64_t qh = a_desc(sQ_hi + k * 32, SM::ROWB), ql = a_desc(sQ_lo + k * 32, SM::ROWB);
-          const uint64_t kh = a_desc(sK_hi + k * 32, SM::ROWB), kl = a_desc(sK_lo + k * 32, SM::ROWB);
-          a_mma(tmem_S, qh, kh, IDESC_S, k > 0 ? 1u : 0u);
-          a_mma(tmem_S, ql, kh, IDESC_S, 1u);
-          a_mma(tmem_S, qh, kl, IDESC_S, 1u);
+          for (int k = 0; k < D / 16; ++k) {
+            a_mma(tmem_S, qh0 + 2 * k, kh0 + 2 * k, IDESC_S, k > 0 ? 1u : 0u);
+            a_mma(tmem_S, ql0 + 2 * k, kh0 + 2 * k, IDESC_S, 1u);
+            a_mma(tmem_S, qh0 + 2 * k, kl0 + 2 * k, IDESC_S, 1u);
+          }
+          a_commit(&bar_s_full);
         }
-        a_commit(&bar_s_full);
+        __syncwarp();
       };
       a_mbar_wait(&bar_q, 0);
       a_mbar_wait(&bar_full[0], 0);
@@ -276,16 +296,18 @@ __global__ void __launch_bounds__(AT_THREADS, (D <= 32) ? 2 : 1) k_attn_tc(const
         a_mbar_wait(&bar_p_full, (uint32_t)(j & 1));        // P(j) is in smem, O block (j-1) was consumed
         a_fence_after();
         const uint32_t sV_hi = sStage0 + stage * SM::STAGE + 2 * SM::K_SLOT, sV_lo = sV_hi + SM::V_SLOT;
+        const uint64_t ph0 = dPV + off16(sP_hi), pl0 = dPV + off16(sP_lo), vh0 = dPV + off16(sV_hi), vl0 = dPV + off16(sV_lo);
+        if (a_elect_one()) {
 #pragma unroll
-        for (int k = 0; k < AT_BKV / 16; ++k) {
-          const uint64_t ph = a_desc(sP_hi + k * 32, 128), pl = a_desc(sP_lo + k * 32, 128);
-          const uint64_t vh = a_desc(sV_hi + k * 32, 128), vl = a_desc(sV_lo + k * 32, 128);
-          a_mma(tmem_O, ph, vh, IDESC_O, k > 0 ? 1u : 0u);
-          a_mma(tmem_O, pl, vh, IDESC_O, 1u);
-          a_mma(tmem_O, ph, vl, IDESC_O, 1u);
+          for (int k = 0; k < AT_BKV / 16; ++k) {
+            a_mma(tmem_O, ph0 + 2 * k, vh0 + 2 * k, IDESC_O, k > 0 ? 1u : 0u);
+            a_mma(tmem_O, pl0 + 2 * k, vh0 + 2 * k, IDESC_O, 1u);
+            a_mma(tmem_O, ph0 + 2 * k, vl0 + 2 * k, IDESC_O, 1u);
+          }
+          a_commit(&bar_o_full);
+          a_commit(&bar_empty[stage]);
         }
-        a_commit(&bar_o_full);
-        a_commit(&bar_empty[stage]);
+        __syncwarp();
         stage = nstage; phase = nphase;
       }
     }

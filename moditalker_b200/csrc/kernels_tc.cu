@@ -364,6 +364,15 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// One lane of a converged warp.  The MMA issuer runs its loop in ALL lanes (uniform control flow) and elects only around the
+// tcgen05 instructions: descriptors computed in warp-uniform code live in uniform registers, whereas inside an `if (lane == 0)`
+// region ptxas wraps every tcgen05.mma in an ELECT / R2UR.BROADCAST waterfall (~115 cycles per MMA measured: the main loop was
+// issue-bound at ~920 cycles per K-iteration with no operand loads at all).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -994,11 +1003,14 @@ __global__ void __launch_bounds__(DIRECT ? TC_THREADS_DIRECT : TC_THREADS, 1) k_
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
   if (dbg && threadIdx.x == 0) s_stamp[1] = clock64();
-  constexpr uint32_t TX_BYTES = DIRECT ? (uint32_t)(2 * BN * 128) : (uint32_t)STAGE;   // bytes TMA delivers per stage
+  // bytes TMA delivers per stage (diagnostic skips: operand halves that are not fetched are not expected either)
+  const uint32_t TX_BYTES = DIRECT ? (uint32_t)(2 * BN * 128)
+                                   : (uint32_t)(((P.dbg_skip & 1) ? 0 : 2 * TC_BM * 128) + ((P.dbg_skip & 2) ? 0 : 2 * BN * 128));
   const int npre = min(NS, it1 - it0);
   const float2* tbl = reinterpret_cast<const float2*>(smem_raw + (smem0 - smem_u32(smem_raw)) + NS * STAGE);
 
   auto load_W = [&](int it, int stage) {
+    if (!DIRECT && (P.dbg_skip & 2)) return;
     const uint32_t sW_hi = smem0 + stage * STAGE + 2 * TC_BM * 128, sW_lo = sW_hi + BN * 128;
     const uint32_t fb = smem_u32(&bar_full[stage]);
     if (it >= it_main) {
@@ -1031,7 +1043,8 @@ __global__ void __launch_bounds__(DIRECT ? TC_THREADS_DIRECT : TC_THREADS, 1) k_
 
   if (warp == 0) {
     // =============================== TMA producer ===============================
-    if (lane == 0) {
+    // whole warp in the loop (uniform coordinates / descriptors stay in uniform registers), one elected lane issues
+    {
       auto load_A = [&](int it, int stage) {
         const uint32_t sA_hi = smem0 + stage * STAGE, sA_lo = sA_hi + TC_BM * 128;
         const uint32_t fb = smem_u32(&bar_full[stage]);
@@ -1045,22 +1058,26 @@ __global__ void __launch_bounds__(DIRECT ? TC_THREADS_DIRECT : TC_THREADS, 1) k_
       // Weights do not depend on the previous kernel: fill the ring's W halves BEFORE the grid
       // dependency resolves (overlaps their HBM latency with the predecessor's tail) ...
       if constexpr (!DIRECT) {
-        for (int i = 0; i < npre; ++i) {
-          mbar_expect_tx(&bar_full[i], TX_BYTES);
-          load_W(it0 + i, i);
+        if (elect_one()) {
+          for (int i = 0; i < npre; ++i) {
+            mbar_expect_tx(&bar_full[i], TX_BYTES);
+            load_W(it0 + i, i);
+          }
         }
+        __syncwarp();
         MTV_PDL_WAIT();                // ... the activation operand does
       }
       int stage = 0; uint32_t phase = 0;
       for (int it = it0; it < it1; ++it) {
+        if (it - it0 >= npre) mbar_wait(&bar_empty[stage], phase ^ 1u);
+        if (dbg && lane == 0 && it == it1 - 1) s_stamp[2] = clock64();          // last stage request issued
+        if (elect_one()) {
         if (it - it0 >= npre) {
-          mbar_wait(&bar_empty[stage], phase ^ 1u);
           mbar_expect_tx(&bar_full[stage], TX_BYTES);
           load_W(it, stage);
         }
-        if (dbg && it == it1 - 1) s_stamp[2] = clock64();          // last stage request issued
         if constexpr (!DIRECT) {
-          load_A(it, stage);
+          if (!(P.dbg_skip & 1)) load_A(it, stage);
         } else {
           // raw fp32 tile of the source that holds this 64-channel chunk (channel concat = two tensors, two map sets)
           const uint32_t rb = smem_u32(&bar_raw[stage]);
@@ -1074,6 +1091,8 @@ __global__ void __launch_bounds__(DIRECT ? TC_THREADS_DIRECT : TC_THREADS, 1) k_
           if (c0 < S.C0) tc_load_A32(g, T, m0, seg1 ? 1 : P.taps, tap, c0, smem0 + stage * STAGE, rb);
           else           tc_load_A32(g, T, m1, seg1 ? 1 : P.taps, tap, c0 - S.C0, smem0 + stage * STAGE, rb);
         }
+        }
+        __syncwarp();
         if (++stage == NS) { stage = 0; phase ^= 1u; }
       }
     }
@@ -1084,26 +1103,32 @@ __global__ void __launch_bounds__(DIRECT ? TC_THREADS_DIRECT : TC_THREADS, 1) k_
     MTV_PDL_TRIGGER();
   } else if (warp == 1) {
     // =============================== MMA issuer =================================
-    if (lane == 0) {
+    // whole warp in the loop, one elected lane issues (see elect_one)
+    {
+      const uint64_t d0 = umma_desc_sw128(smem0);                   // descriptor of the ring's first byte; tiles are +offset/16
       int stage = 0; uint32_t phase = 0;
       for (int it = it0; it < it1; ++it) {
         mbar_wait(&bar_full[stage], phase);
-        if (dbg && it == it0) s_stamp[3] = clock64();               // first operands landed
-        if (dbg && it == it1 - 1) s_stamp[4] = clock64();           // last operands landed
+        if (dbg && lane == 0 && it == it0) s_stamp[3] = clock64();       // first operands landed
+        if (dbg && lane == 0 && it == it1 - 1) s_stamp[4] = clock64();   // last operands landed
         tc_fence_after();
-        const uint32_t sA_hi = smem0 + stage * STAGE, sA_lo = sA_hi + TC_BM * 128;
-        const uint32_t sW_hi = sA_lo + TC_BM * 128;
+        const uint64_t dA = d0 + (uint64_t)((uint32_t)(stage * STAGE) >> 4);
+        const uint32_t acc0 = it > it0 ? 1u : 0u;
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < TC_BK / 16; ++k) {
-          const uint64_t a_hi = umma_desc_sw128(sA_hi + k * 32), a_lo = umma_desc_sw128(sA_lo + k * 32);
-          const uint64_t w_hi = umma_desc_sw128(sW_hi + k * 32);          // rows [0,BN) = W_hi, [BN,2BN) = W_lo
-          umma_bf16(tmem_base, a_hi, w_hi, IDESC2, (it > it0 || k > 0) ? 1u : 0u);
-          umma_bf16(tmem_base, a_lo, w_hi, IDESC, 1u);
+          for (int k = 0; k < TC_BK / 16; ++k) {
+            const uint64_t a_hi = dA + (uint64_t)(k * 2), a_lo = a_hi + (uint64_t)((TC_BM * 128) >> 4);
+            const uint64_t w_hi = a_hi + (uint64_t)((2 * TC_BM * 128) >> 4);    // rows [0,BN) = W_hi, [BN,2BN) = W_lo
+            umma_bf16(tmem_base, a_hi, w_hi, IDESC2, k > 0 ? 1u : acc0);
+            umma_bf16(tmem_base, a_lo, w_hi, IDESC, 1u);
+          }
+          umma_commit(&bar_empty[stage]);        // frees the smem slot once these MMAs have read it
         }
-        umma_commit(&bar_empty[stage]);          // frees the smem slot once these MMAs have read it
+        __syncwarp();
         if (++stage == NS) { stage = 0; phase ^= 1u; }
       }
-      umma_commit(&bar_acc);                      // accumulator complete
+      if (elect_one()) umma_commit(&bar_acc);     // accumulator complete
+      __syncwarp();
     }
     mbar_wait(&bar_acc, 0);
     MTV_PDL_TRIGGER();
@@ -1455,7 +1480,9 @@ __device__ __noinline__ void chain_gemm(const TcConvParams& PG, const TcConvPara
     }
   } else if (warp == 1) {
     // =============================== MMA issuer =================================
-    if (lane == 0) {
+    // whole warp in the loop, one elected lane issues (see elect_one)
+    {
+      const uint64_t d0 = umma_desc_sw128(smem0);
       int stage = 0; uint32_t phase = 0, tl = 0;
       for (int tile = blockIdx.x; tile < G.ntiles; tile += gridDim.x) {
         const int z = (tile / G.mt) / G.nt;
@@ -1465,19 +1492,23 @@ __device__ __noinline__ void chain_gemm(const TcConvParams& PG, const TcConvPara
         for (int it = it0; it < it1; ++it) {
           mbar_wait(&bar_full[stage], phase);
           tc_fence_after();
-          const uint32_t sA_hi = smem0 + stage * STAGE, sA_lo = sA_hi + TC_BM * 128;
-          const uint32_t sW_hi = sA_lo + TC_BM * 128;
+          const uint64_t dA = d0 + (uint64_t)((uint32_t)(stage * STAGE) >> 4);
+          const uint32_t acc0 = it > it0 ? 1u : 0u;
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < TC_BK / 16; ++k) {
-            const uint64_t a_hi = umma_desc_sw128(sA_hi + k * 32), a_lo = umma_desc_sw128(sA_lo + k * 32);
-            const uint64_t w_hi = umma_desc_sw128(sW_hi + k * 32);          // rows [0,BN) = W_hi, [BN,2BN) = W_lo
-            umma_bf16(tmem_base, a_hi, w_hi, IDESC2, (it > it0 || k > 0) ? 1u : 0u);
-            umma_bf16(tmem_base, a_lo, w_hi, IDESC, 1u);
+            for (int k = 0; k < TC_BK / 16; ++k) {
+              const uint64_t a_hi = dA + (uint64_t)(k * 2), a_lo = a_hi + (uint64_t)((TC_BM * 128) >> 4);
+              const uint64_t w_hi = a_hi + (uint64_t)((2 * TC_BM * 128) >> 4);    // rows [0,BN) = W_hi, [BN,2BN) = W_lo
+              umma_bf16(tmem_base, a_hi, w_hi, IDESC2, k > 0 ? 1u : acc0);
+              umma_bf16(tmem_base, a_lo, w_hi, IDESC, 1u);
+            }
+            umma_commit(&bar_empty[stage]);
           }
-          umma_commit(&bar_empty[stage]);
+          __syncwarp();
           if (++stage == NS) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(bar_acc);
+        if (elect_one()) umma_commit(bar_acc);
+        __syncwarp();
         ++tl;
       }
     }

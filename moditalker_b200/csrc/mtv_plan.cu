@@ -170,9 +170,9 @@ struct MtvHandle_t {
   int64_t weight_bytes = 0;
   // feature bits (MTV_TC_MASK): 0-4 op classes on the tensor-core kernel, 5 split-K, 6 tcgen05 attention, 7 small levels,
   // 8 fused GroupNorm statistics, 9 launch fusions, 10 weight L2 prefetch, 11 L2-persisting small-tensor arena;
-  // 14 consumer GroupNorm + apply fused into small-level split-K reductions;
+  // 14 consumer GroupNorm + apply fused into small-level split-K reductions, 15 BN = 128 tiles for every split-K-able op;
   // opt-in (measured slower on B200, kept for A/B — profiles/r01_s2_*.md): 12 persistent chain kernel, 13 direct A operand
-  int tc_mask = 0x4fff;
+  int tc_mask = 0xcfff;
   cudaStream_t cap_stream = nullptr;
   cudaStream_t capture_stream() {
     if (!cap_stream) CK(cudaStreamCreateWithFlags(&cap_stream, cudaStreamNonBlocking));
@@ -580,8 +580,16 @@ struct Builder {
     T.bias = P.bias; T.resid = P.resid; T.resid_mode = P.resid_mode; T.out = P.out;
     const int M = B * P.geo.L;
     const int mtiles = P.geo.L > 128 ? M / 128 : (B + (128 / P.geo.L) - 1) / (128 / P.geo.L);
+    // BN = 128 (stacked N = 256) runs the tensor pipe ~1.6x more efficiently per FLOP than BN = 64 (a K-iteration costs ~1200
+    // vs ~1000 cycles for twice the work, profiles/r01_s2_mainloop_skip.md): take it once the SMs are covered, or whenever the
+    // op is deep enough for split-K to restore the CTA count
+    const int iters_all = S.taps * ((S.C0 + S.C1) / 64) + (P.nsegs == 2 ? (P.seg[1].C0 + P.seg[1].C1) / 64 : 0);
     int bn = 64;
-    if (P.Cout % 128 == 0 && mtiles * (P.Cout / 128) >= 64) bn = 128;   // fewer smem bytes per MMA once the SMs are covered
+    if (P.Cout % 128 == 0) {
+      const int base128 = mtiles * (P.Cout / 128);
+      const bool splittable = iters_all >= 16 && ((h->tc_mask >> 5) & 1) && !o.qkv && base128 * 2 <= h->num_sms + h->num_sms / 4;
+      if (base128 >= 64 || (splittable && ((h->tc_mask >> 15) & 1))) bn = 128;
+    }
     T.bn = bn;
     const bool direct = use_direct() && !o.pre0 && !o.pre1 && !o.raw_out && direct_seg_ok(S, norm0, P.geo) &&
                         (P.nsegs == 1 || (norm1 < 0 && !P.seg[1].silu && direct_seg_ok(P.seg[1], -1, P.geo)));
@@ -633,6 +641,7 @@ struct Builder {
     Op op; op.name = "conv_tc:" + name; op.launches = ks > 1 ? 2 : 1;
     op.flops = 2.0 * M * P.Cout * Ktot;
     op.bytes = 4.0 * Ktot * P.Cout + 4.0 * M * Ktot / S.taps + 4.0 * M * P.Cout;
+    if (const char* ds = getenv("MTV_TC_DBG_SKIP")) T.dbg_skip = atoi(ds);
     auto tp = std::make_shared<TcConvParams>(T);
     op.fn = [tp](cudaStream_t s) { return launch_conv_tc(*tp, s); };
     op.tc = tp;
