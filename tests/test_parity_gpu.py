@@ -160,8 +160,9 @@ def test_launch_modes_do_not_change_results(monkeypatch):
     outs = {}
     for name, env in (("pdl default", {}), ("pdl off", {"MTV_PDL": "0"}), ("pdl all", {"MTV_PDL": "31"}),
                       ("no graph", {"MTV_NO_GRAPH": "1"}),
-                      ("chain kernel", {"MTV_TC_MASK": "0x1fff"}), ("chain kernel, pdl off", {"MTV_TC_MASK": "0x1fff", "MTV_PDL": "0"}),
-                      ("direct A operand", {"MTV_TC_MASK": "0x2fff"})):
+                      # opt-in paths = default feature mask (0xcfff) + their bit: same tiles, same summation order
+                      ("chain kernel", {"MTV_TC_MASK": "0xdfff"}), ("chain kernel, pdl off", {"MTV_TC_MASK": "0xdfff", "MTV_PDL": "0"}),
+                      ("direct A operand", {"MTV_TC_MASK": "0xefff"})):
         for k in ("MTV_PDL", "MTV_NO_GRAPH", "MTV_TC_MASK"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
