@@ -82,6 +82,21 @@ __device__ __forceinline__ bool a_elect_one() {
   asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
   return pred != 0;
 }
+// A operand from tensor memory (lane = row, each 32-bit column = two consecutive K elements; K = 16 -> 8 columns per MMA)
+__device__ __forceinline__ void a_mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void a_tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+__device__ __forceinline__ void a_tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void a_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(a_smem_u32(bar)) : "memory");
 }
@@ -165,6 +180,13 @@ cudaError_t launch_qkv_split(const QkvSplitParams& P, cudaStream_t s) {
 
 // ------------------------------------------------------------------ attention
 constexpr int AT_BQ = 128, AT_BKV = 64, AT_THREADS = 320, AT_NS = 3;   // warps: 0 TMA, 1 MMA, 2-5 / 6-9 softmax halves
+// P (softmax probabilities, split bf16) is handed to the PV MMA through TENSOR MEMORY (tcgen05.st by the softmax threads, A operand
+// of tcgen05.mma read from TMEM): the kernel was shared-memory-bandwidth bound at head dim 16 — per 64-key block 32 KB of P stores
+// and 48 KB of MMA re-reads of P against 8 KB of K / V — and "no P stores" alone was worth -21 % (profiles/r01_s2_attention_skip.md)
+#ifndef MTV_ATTN_P_IN_TMEM
+#define MTV_ATTN_P_IN_TMEM 1
+#endif
+constexpr bool AT_P_IN_TMEM = MTV_ATTN_P_IN_TMEM != 0;
 
 template <int D>
 struct AttnSmem {
@@ -175,8 +197,8 @@ struct AttnSmem {
   static constexpr int align_up(int v) { return (v + 1023) & ~1023; }
   static constexpr int Q_SLOT = align_up(Q_BYTES), K_SLOT = align_up(K_BYTES), V_SLOT = align_up(V_BYTES);
   static constexpr int STAGE = 2 * K_SLOT + 2 * V_SLOT;
-  static constexpr int P_SLOT = AT_BQ * 128;               // P tile: 128 rows x 64 keys bf16
-  static constexpr int TOTAL = 2 * Q_SLOT + AT_NS * STAGE + 2 * P_SLOT + 1024;
+  static constexpr int P_SLOT = AT_BQ * 128;               // P tile: 128 rows x 64 keys bf16 (only when P goes through smem)
+  static constexpr int TOTAL = 2 * Q_SLOT + AT_NS * STAGE + (AT_P_IN_TMEM ? 0 : 2 * P_SLOT) + 1024;
   static constexpr int STAGE_TX = 2 * K_BYTES + 2 * V_BYTES;
 };
 
@@ -186,7 +208,8 @@ __global__ void __launch_bounds__(AT_THREADS, (D <= 32) ? 2 : 1) k_attn_tc(const
   mtv_prefetch_slice(P.pf0, P.pf1, P.pf_bytes, blockIdx.x + gridDim.x * blockIdx.y, gridDim.x * gridDim.y);
   constexpr uint32_t IDESC_S = a_idesc(AT_BQ, AT_BKV);
   constexpr uint32_t IDESC_O = a_idesc(AT_BQ, D);
-  constexpr int TMEM_COLS = 128;                           // S: cols [0,64), O block: cols [64, 64+D)
+  // S: cols [0,64), O block: cols [64, 64+D), P_hi: [128,160), P_lo: [160,192) (bf16 pairs, 64 keys)
+  constexpr int TMEM_COLS = AT_P_IN_TMEM ? 256 : 128;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_q, bar_full[AT_NS], bar_empty[AT_NS], bar_s_full, bar_s_free, bar_p_full, bar_o_full;
   __shared__ uint32_t tmem_base_s;
@@ -214,7 +237,8 @@ __global__ void __launch_bounds__(AT_THREADS, (D <= 32) ? 2 : 1) k_attn_tc(const
     a_mbar_init(&bar_q, 1);
     for (int s = 0; s < AT_NS; ++s) { a_mbar_init(&bar_full[s], 1); a_mbar_init(&bar_empty[s], 1); }
     a_mbar_init(&bar_s_full, 1); a_mbar_init(&bar_o_full, 1);
-    a_mbar_init(&bar_s_free, 256); a_mbar_init(&bar_p_full, 256);
+    // one arrival per softmax WARP (8), not per thread: 256 same-address mbarrier arrivals per key block serialise in shared memory
+    a_mbar_init(&bar_s_free, 8); a_mbar_init(&bar_p_full, 8);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -227,6 +251,7 @@ __global__ void __launch_bounds__(AT_THREADS, (D <= 32) ? 2 : 1) k_attn_tc(const
   a_fence_after();
   const uint32_t tmem_base = tmem_base_s;
   const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 64;
+  const uint32_t tmem_Phi = tmem_base + 128, tmem_Plo = tmem_base + 160;
   MTV_PDL_WAIT();        // Q / K / V^T are written by the preceding k_qkv_split
 
   if (warp == 0) {
@@ -300,9 +325,15 @@ __global__ void __launch_bounds__(AT_THREADS, (D <= 32) ? 2 : 1) k_attn_tc(const
         if (a_elect_one()) {
 #pragma unroll
           for (int k = 0; k < AT_BKV / 16; ++k) {
-            a_mma(tmem_O, ph0 + 2 * k, vh0 + 2 * k, IDESC_O, k > 0 ? 1u : 0u);
-            a_mma(tmem_O, pl0 + 2 * k, vh0 + 2 * k, IDESC_O, 1u);
-            a_mma(tmem_O, ph0 + 2 * k, vl0 + 2 * k, IDESC_O, 1u);
+            if constexpr (AT_P_IN_TMEM) {
+              a_mma_ts(tmem_O, tmem_Phi + 8 * k, vh0 + 2 * k, IDESC_O, k > 0 ? 1u : 0u);
+              a_mma_ts(tmem_O, tmem_Plo + 8 * k, vh0 + 2 * k, IDESC_O, 1u);
+              a_mma_ts(tmem_O, tmem_Phi + 8 * k, vl0 + 2 * k, IDESC_O, 1u);
+            } else {
+              a_mma(tmem_O, ph0 + 2 * k, vh0 + 2 * k, IDESC_O, k > 0 ? 1u : 0u);
+              a_mma(tmem_O, pl0 + 2 * k, vh0 + 2 * k, IDESC_O, 1u);
+              a_mma(tmem_O, ph0 + 2 * k, vl0 + 2 * k, IDESC_O, 1u);
+            }
           }
           a_commit(&bar_o_full);
           a_commit(&bar_empty[stage]);
@@ -350,7 +381,8 @@ __global__ void __launch_bounds__(AT_THREADS, (D <= 32) ? 2 : 1) k_attn_tc(const
         for (int i = 0; i < 32; ++i) s[i] = __uint_as_float(r[i]);
       }
       a_fence_before();
-      a_mbar_arrive(&bar_s_free);                           // S TMEM may be overwritten by S(j+1)
+      __syncwarp();
+      if (lane == 0) a_mbar_arrive(&bar_s_free);            // S TMEM may be overwritten by S(j+1)
       const int valid = len - j * AT_BKV - half * 32;       // >= 32 except in the last block (may be <= 0 there)
       if (valid < 32) {
 #pragma unroll
@@ -360,21 +392,28 @@ __global__ void __launch_bounds__(AT_THREADS, (D <= 32) ? 2 : 1) k_attn_tc(const
 #pragma unroll
       for (int i = 2; i < 32; ++i) mx = fmaxf(mx, s[i]);
       // row max over both halves
+      if (!(P.dbg_skip & 4)) {
       s_xchg[j & 1][half][row] = mx;
       asm volatile("bar.sync 1, 256;" ::: "memory");
       mx = fmaxf(mx, s_xchg[j & 1][half ^ 1][row]);
+      }
       const float m_new = fmaxf(m_run, mx);                 // finite: the lower half always holds a valid key
       const float corr = ex2_approx(m_run - m_new);
       float sum0 = 0.f, sum1 = 0.f;
+      if (!(P.dbg_skip & 1)) {
 #pragma unroll
       for (int i = 0; i < 32; i += 2) {
         s[i] = ex2_approx(s[i] - m_new); s[i + 1] = ex2_approx(s[i + 1] - m_new);
         sum0 += s[i]; sum1 += s[i + 1];
       }
+      } else {
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) { s[i] = s[i] - m_new; s[i + 1] = s[i + 1] - m_new; sum0 += s[i]; sum1 += s[i + 1]; }
+      }
       if (j > 0) {                                          // O block (j-1) finished -> fold it in before rescaling
         a_mbar_wait(&bar_o_full, (uint32_t)((j - 1) & 1));
         a_fence_after();
-        fold_O();
+        if (!(P.dbg_skip & 8)) fold_O();
       }
       l_part = l_part * corr + (sum0 + sum1);
       m_run = m_new;
@@ -382,7 +421,21 @@ __global__ void __launch_bounds__(AT_THREADS, (D <= 32) ? 2 : 1) k_attn_tc(const
       for (int d = 0; d < DH; ++d) o[d] *= corr;
       // P(j) -> smem, split bf16, 128B-swizzled K-major rows (16-byte chunk c of row r at c ^ (r & 7));
       // this half owns chunks [4*half, 4*half + 4).  hi = bf16x2(p), lo = bf16x2(p - float(hi)): 3 instr / element
-      {
+      if constexpr (AT_P_IN_TMEM) {
+        // this thread's 32 keys of its row -> 16 packed columns each of P_hi / P_lo (key 2e in the low half of column e)
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const float p0 = s[2 * e], p1 = s[2 * e + 1];
+          hi[e] = cvt_bf16x2(p0, p1);
+          lo[e] = cvt_bf16x2(p0 - __uint_as_float(hi[e] << 16), p1 - __uint_as_float(hi[e] & 0xffff0000u));
+        }
+        if (!(P.dbg_skip & 2)) {
+          a_tmem_st16(tmem_Phi + lane_addr + (uint32_t)(half * 16), hi);
+          a_tmem_st16(tmem_Plo + lane_addr + (uint32_t)(half * 16), lo);
+          a_tmem_wait_st();
+        }
+      } else if (!(P.dbg_skip & 2)) {   // P through shared memory
         const uint32_t rbase_hi = sP_hi + (uint32_t)row * 128u, rbase_lo = sP_lo + (uint32_t)row * 128u;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
@@ -398,9 +451,10 @@ __global__ void __launch_bounds__(AT_THREADS, (D <= 32) ? 2 : 1) k_attn_tc(const
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rbase_lo + off), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
         }
       }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA (async proxy)
+      if (!AT_P_IN_TMEM) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA (async proxy)
       a_fence_before();
-      a_mbar_arrive(&bar_p_full);
+      __syncwarp();
+      if (lane == 0) a_mbar_arrive(&bar_p_full);
       // s_xchg is double-buffered by block parity: slot (j & 1) is rewritten in block j + 2, i.e. after the
       // bar.sync of block j + 1, which every reader of block j has passed by then
     }

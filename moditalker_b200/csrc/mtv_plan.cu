@@ -853,6 +853,7 @@ struct Builder {
     Tensor att; SplitBuf att_split;
     if (tc_attn) {
       AttnTcParams T{}; T.B = B; T.L = L; T.C = C; T.heads = heads; T.nseg = A.nseg;
+      if (const char* ds = getenv("MTV_ATTN_DBG_SKIP")) T.dbg_skip = atoi(ds);
       for (int i = 0; i < 4; ++i) T.seg_off[i] = A.seg_off[i];
       if (fuse) {
         const size_t bytes = (size_t)B * L * C * 2;

@@ -105,6 +105,7 @@ struct AttnTcParams {
   const void* pf0; const void* pf1; unsigned long long pf_bytes;   // L2 prefetch of the proj_out weights
   int B, L, C, heads;
   int nseg; int seg_off[4];
+  int dbg_skip;   // diagnostics only (MTV_ATTN_DBG_SKIP; results are garbage): 1 no exp2, 2 no P stores, 4 no row-max exchange, 8 no O fold
 };
 cudaError_t launch_qkv_split(const QkvSplitParams& P, cudaStream_t s);
 cudaError_t launch_attn_tc(const AttnTcParams& P, cudaStream_t s);
