@@ -125,6 +125,13 @@ __device__ __forceinline__ uint32_t cvt_bf16x2(float e0, float e1) {
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(e1), "f"(e0));
   return d;
 }
+// packed fp32 pairs (sm_100 FADD2 / FMUL2): the softmax warps are instruction-issue bound, these halve the add / mul count
+__device__ __forceinline__ uint64_t f2_pack(float lo, float hi) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t f2_sub(uint64_t a, uint64_t b) { uint64_t r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) { uint64_t r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) { uint64_t r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ float max3(float a, float b, float c) { float d; asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c)); return d; }
 __device__ __forceinline__ float ex2_approx(float x) {   // 2^x, max rel. error 2^-22; 2^-inf = 0
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -365,7 +372,8 @@ __global__ void __launch_bounds__(AT_THREADS, (D <= 32) ? 2 : 1) k_attn_tc(const
         a_tmem_ld8(tmem_O + lane_addr + (uint32_t)(half * DH + c), r);
         a_tmem_wait_ld();
 #pragma unroll
-        for (int i = 0; i < 8; ++i) o[c + i] += __uint_as_float(r[i]);
+        for (int i = 0; i < 8; i += 2)
+          f2_unpack(f2_add(f2_pack(o[c + i], o[c + i + 1]), f2_pack(__uint_as_float(r[i]), __uint_as_float(r[i + 1]))), o[c + i], o[c + i + 1]);
       }
     };
 
@@ -390,7 +398,7 @@ __global__ void __launch_bounds__(AT_THREADS, (D <= 32) ? 2 : 1) k_attn_tc(const
       }
       float mx = fmaxf(s[0], s[1]);
 #pragma unroll
-      for (int i = 2; i < 32; ++i) mx = fmaxf(mx, s[i]);
+      for (int i = 2; i < 32; i += 2) mx = max3(mx, s[i], s[i + 1]);
       // row max over both halves
       if (!(P.dbg_skip & 4)) {
       s_xchg[j & 1][half][row] = mx;
@@ -401,11 +409,15 @@ __global__ void __launch_bounds__(AT_THREADS, (D <= 32) ? 2 : 1) k_attn_tc(const
       const float corr = ex2_approx(m_run - m_new);
       float sum0 = 0.f, sum1 = 0.f;
       if (!(P.dbg_skip & 1)) {
+        const uint64_t mm = f2_pack(m_new, m_new);
+        uint64_t sums = f2_pack(0.f, 0.f);
 #pragma unroll
-      for (int i = 0; i < 32; i += 2) {
-        s[i] = ex2_approx(s[i] - m_new); s[i + 1] = ex2_approx(s[i + 1] - m_new);
-        sum0 += s[i]; sum1 += s[i + 1];
-      }
+        for (int i = 0; i < 32; i += 2) {
+          float x0, x1; f2_unpack(f2_sub(f2_pack(s[i], s[i + 1]), mm), x0, x1);
+          s[i] = ex2_approx(x0); s[i + 1] = ex2_approx(x1);
+          sums = f2_add(sums, f2_pack(s[i], s[i + 1]));
+        }
+        f2_unpack(sums, sum0, sum1);
       } else {
 #pragma unroll
       for (int i = 0; i < 32; i += 2) { s[i] = s[i] - m_new; s[i + 1] = s[i + 1] - m_new; sum0 += s[i]; sum1 += s[i + 1]; }
@@ -417,8 +429,11 @@ __global__ void __launch_bounds__(AT_THREADS, (D <= 32) ? 2 : 1) k_attn_tc(const
       }
       l_part = l_part * corr + (sum0 + sum1);
       m_run = m_new;
+      {
+        const uint64_t cc = f2_pack(corr, corr);
 #pragma unroll
-      for (int d = 0; d < DH; ++d) o[d] *= corr;
+        for (int d = 0; d < DH; d += 2) f2_unpack(f2_mul(f2_pack(o[d], o[d + 1]), cc), o[d], o[d + 1]);
+      }
       // P(j) -> smem, split bf16, 128B-swizzled K-major rows (16-byte chunk c of row r at c ^ (r & 7));
       // this half owns chunks [4*half, 4*half + 4).  hi = bf16x2(p), lo = bf16x2(p - float(hi)): 3 instr / element
       if constexpr (AT_P_IN_TMEM) {
@@ -428,7 +443,9 @@ __global__ void __launch_bounds__(AT_THREADS, (D <= 32) ? 2 : 1) k_attn_tc(const
         for (int e = 0; e < 16; ++e) {
           const float p0 = s[2 * e], p1 = s[2 * e + 1];
           hi[e] = cvt_bf16x2(p0, p1);
-          lo[e] = cvt_bf16x2(p0 - __uint_as_float(hi[e] << 16), p1 - __uint_as_float(hi[e] & 0xffff0000u));
+          float l0, l1;
+          f2_unpack(f2_sub(f2_pack(p0, p1), f2_pack(__uint_as_float(hi[e] << 16), __uint_as_float(hi[e] & 0xffff0000u))), l0, l1);
+          lo[e] = cvt_bf16x2(l0, l1);
         }
         if (!(P.dbg_skip & 2)) {
           a_tmem_st16(tmem_Phi + lane_addr + (uint32_t)(half * 16), hi);
