@@ -5,8 +5,11 @@ mkdir -p gpurun_out
 python __graft_entry__.py > gpurun_out/build.log 2>&1
 K='regex:k_(conv|attn|gn_|splitk|linear|temb|pack|ddim|apply|tc_|qkv)'
 for b in 1 8; do
+  # skip the three warm-up steps (plan launches + pack_in + ddim_step each), capture the timed step
+  n=$(python -c "import torch;from moditalker_b200 import BASE_UNET_CONFIG as C,DiffusionWrapper as W,UNetModel as U;from moditalker_b200.synth import synth_state_dict as S;m=W(U(**C));m.load_state_dict(S(C,0,'diffusion_model.'));m=m.cuda().eval();print(m.diffusion_model.plan_info($b)['launches'])" 2>/dev/null | tail -1)
+  echo "launches per step (B=$b): $n" | tee -a gpurun_out/summary.txt
   timeout 500 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --cache-control none \
-      -k "$K" -s ${SKIP:-945} -c 330 --csv --log-file gpurun_out/launches_b${b}.csv \
+      -k "$K" -s $((3 * n)) -c $n --csv --log-file gpurun_out/launches_b${b}.csv \
       env MTV_NO_GRAPH=1 python bench.py --steps 1 --warmup 3 --no-cpu-baseline --chunks-per-gpu $b > gpurun_out/ncu_b${b}.log 2>&1
   echo "ncu list b$b rc=$?" | tee -a gpurun_out/summary.txt
 done
