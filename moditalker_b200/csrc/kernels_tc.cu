@@ -428,7 +428,9 @@ __device__ __forceinline__ void ld_global_nc_v8(const float* p, float* v) {
 }
 
 // ------------------------------------------------------------------ the tap-GEMM
-constexpr int TC_BM = 128, TC_BK = 64, TC_THREADS = 192;
+// warps: 0 TMA, 1 MMA, 2-9 epilogue (two warps per TMEM lane quarter, each taking every other 32-column chunk: the
+// row-per-lane epilogue is instruction-issue bound and was the longest phase of the small-batch GEMMs with four warps)
+constexpr int TC_BM = 128, TC_BK = 64, TC_THREADS = 320;
 __host__ __device__ constexpr int tc_stage_bytes(int BN) { return 2 * TC_BM * 128 + 2 * BN * 128; }
 __host__ __device__ constexpr int tc_stages(int BN) { return BN == 64 ? 4 : 3; }
 __host__ __device__ constexpr int tc_smem_bytes(int BN) { return tc_stages(BN) * tc_stage_bytes(BN) + 1024; }
@@ -779,11 +781,14 @@ __device__ __forceinline__ void tc_produce_A(const TcConvParams& P, const Geo& g
 // The tap-GEMM epilogue (warps 2-5 of the CTA): TMEM -> registers -> (+bias, +residual, GroupNorm sums | qkv operand
 // split | split-K partial) -> HBM.  Shared by the one-tile-per-CTA kernel (PDL = true: it owns the grid-dependency
 // wait / trigger) and the persistent chain kernel (PDL = false: several tiles per CTA, s_bias is reused).
-template <int BN, int EPI, bool PDL>
+// EW = number of epilogue warps (4: warps 2-5; 8: warps 2-9, warp group (warp-2)/4 takes chunks group, group+2, ...).
+template <int BN, int EPI, bool PDL, int EW>
 __device__ __forceinline__ void tc_epilogue(const TcConvParams& P, const Geo& g, const TcTile& T, int n0, int zidx,
                                             uint32_t tmem_base, float* s_bias, uint64_t* bar_acc, uint32_t acc_parity,
                                             long long* stamp) {
+  constexpr int CSTEP = 32 * (EW / 4);          // column stride between the chunks of one warp
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cfirst = ((warp - 2) >> 2) * 32;    // first chunk of this warp (0 when EW == 4)
   const int q = warp & 3;                       // TMEM lane quarter this warp may read
   const int row = q * 32 + lane;                // row of the tile
   int b, tok; tc_row_map(T, row, b, tok);
@@ -794,16 +799,16 @@ __device__ __forceinline__ void tc_epilogue(const TcConvParams& P, const Geo& g,
   // miss (~2000 cycles) if loaded on demand per chunk — so it is staged in smem during the main loop.
   {
     const int te = threadIdx.x - 64;
-    if (!PDL) asm volatile("bar.sync 1, 128;" ::: "memory");   // persistent caller: the previous tile's readers of s_bias are done
+    if (!PDL) asm volatile("bar.sync 1, %0;" ::"n"(32 * EW) : "memory");   // persistent caller: the previous tile's readers of s_bias are done
     if (te < BN) s_bias[te] = P.bias ? __ldg(P.bias + n0 + te) : 0.0f;
-    asm volatile("bar.sync 1, 128;" ::: "memory");
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * EW) : "memory");
   }
   // the residual of the first 32-column chunk is fetched while the MMAs still run
   const bool pre_res = EPI == 1 && live && P.resid;
   float rpre[32];
   if (pre_res) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) ld_global_nc_v8(P.resid + m * P.Cout + n0 + 8 * j, rpre + 8 * j);
+    for (int j = 0; j < 4; ++j) ld_global_nc_v8(P.resid + m * P.Cout + n0 + cfirst + 8 * j, rpre + 8 * j);
   }
   mbar_wait(bar_acc, acc_parity);
   if (PDL) MTV_PDL_TRIGGER();
@@ -813,7 +818,7 @@ __device__ __forceinline__ void tc_epilogue(const TcConvParams& P, const Geo& g,
   if (EPI == 3 || ((EPI == 1) && P.csum)) tc_decode_fast(T, tok, p, y, x);
   const int pl_stat = p;
 #pragma unroll 1
-  for (int c0 = 0; c0 < BN; c0 += 32) {
+  for (int c0 = cfirst; c0 < BN; c0 += CSTEP) {
     uint32_t r[32];
     __syncwarp();
     {
@@ -831,10 +836,10 @@ __device__ __forceinline__ void tc_epilogue(const TcConvParams& P, const Geo& g,
 #pragma unroll
     for (int j = 0; j < 8; ++j) bpre[j] = *reinterpret_cast<const float4*>(&s_bias[c0 + 4 * j]);
     float rnext[32];
-    const bool have_next = pre_res && (c0 + 32 < BN);
+    const bool have_next = pre_res && (c0 + CSTEP < BN);
     if (have_next) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) ld_global_nc_v8(P.resid + m * P.Cout + n + 32 + 8 * j, rnext + 8 * j);
+      for (int j = 0; j < 4; ++j) ld_global_nc_v8(P.resid + m * P.Cout + n + CSTEP + 8 * j, rnext + 8 * j);
     }
     if (!live) {
       // rows of samples beyond the batch (partial last tile of a small level): nothing to store
@@ -879,8 +884,10 @@ __device__ __forceinline__ void tc_epilogue(const TcConvParams& P, const Geo& g,
         fv[j] = v.x; fv[j + 1] = v.y; fv[j + 2] = v.z; fv[j + 3] = v.w;
       }
       if constexpr (EPI != 2) {
+        if (!(P.dbg_skip & 8)) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 8) st_global_v8(dst + j, fv + j);
+          for (int j = 0; j < 32; j += 8) st_global_v8(dst + j, fv + j);
+        }
       }
       if constexpr (EPI == 2) {
         // channels are head-major [h: q(D) k(D) v(D)] (unet.py:321); D >= 16, so every aligned run of 16
@@ -920,7 +927,7 @@ __device__ __forceinline__ void tc_epilogue(const TcConvParams& P, const Geo& g,
         for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(fv[j]);
       }
     }
-    if ((EPI == 1 || EPI == 3) && P.csum) {
+    if ((EPI == 1 || EPI == 3) && P.csum && !(P.dbg_skip & 4)) {
       float fv[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) fv[j] = __uint_as_float(r[j]);
@@ -1137,12 +1144,7 @@ __global__ void __launch_bounds__(DIRECT ? TC_THREADS_DIRECT : TC_THREADS, 1) k_
       const int pw = warp - 2;                    // producer warp 0..7: group = pw >> 2
       tc_produce_A<BN>(P, g, T, it0, it1, it_main, kch, smem0, bar_raw, bar_full, tbl, s_rowinfo, pw >> 2, (pw & 3) * 32 + lane, dbg ? s_pstamp : nullptr);
     }
-    if (!DIRECT || warp < 6) {
-      tc_epilogue<BN, EPI, true>(P, g, T, n0, (int)blockIdx.z, tmem_base, s_bias, &bar_acc, 0u, dbg ? s_stamp : nullptr);
-    } else {
-      mbar_wait(&bar_acc, 0);
-      MTV_PDL_TRIGGER();
-    }
+    tc_epilogue<BN, EPI, true, 8>(P, g, T, n0, (int)blockIdx.z, tmem_base, s_bias, &bar_acc, 0u, dbg ? s_stamp : nullptr);
   }
   if (dbg && threadIdx.x == 64) s_stamp[6] = clock64();              // epilogue stores issued
   tc_fence_before();
@@ -1520,10 +1522,10 @@ __device__ __noinline__ void chain_gemm(const TcConvParams& PG, const TcConvPara
       const int mx = tile % G.mt, r = tile / G.mt, n0 = (r % G.nt) * BN, z = r / G.nt;
       const TcTile T = tc_tile(g, mx);
       switch (epi) {
-        case 0: tc_epilogue<BN, 0, false>(P, g, T, n0, z, tmem_base, s_bias, bar_acc, tl & 1u, nullptr); break;
-        case 1: tc_epilogue<BN, 1, false>(P, g, T, n0, z, tmem_base, s_bias, bar_acc, tl & 1u, nullptr); break;
-        case 2: tc_epilogue<BN, 2, false>(P, g, T, n0, z, tmem_base, s_bias, bar_acc, tl & 1u, nullptr); break;
-        default: tc_epilogue<BN, 3, false>(P, g, T, n0, z, tmem_base, s_bias, bar_acc, tl & 1u, nullptr); break;
+        case 0: tc_epilogue<BN, 0, false, 4>(P, g, T, n0, z, tmem_base, s_bias, bar_acc, tl & 1u, nullptr); break;
+        case 1: tc_epilogue<BN, 1, false, 4>(P, g, T, n0, z, tmem_base, s_bias, bar_acc, tl & 1u, nullptr); break;
+        case 2: tc_epilogue<BN, 2, false, 4>(P, g, T, n0, z, tmem_base, s_bias, bar_acc, tl & 1u, nullptr); break;
+        default: tc_epilogue<BN, 3, false, 4>(P, g, T, n0, z, tmem_base, s_bias, bar_acc, tl & 1u, nullptr); break;
       }
       tc_fence_before();
       __syncwarp();
