@@ -572,6 +572,25 @@ __device__ __forceinline__ void tc_csum_chunk32(float (&v)[32], bool live, int l
   }
 }
 
+// ------------------------------------------------------------------ TMA store of an epilogue sub-tile
+// Each epilogue warp stages its 32 rows x 32 fp32 columns in (idle) operand-ring memory, 128B-swizzled, and ONE elected lane
+// writes them with a bulk tensor store: whole 128-byte lines per request instead of 32 scattered 32-byte row segments per
+// st.global instruction (which cost ~1800 cycles per chunk, profiles/r01_s2_mainloop_skip.md).
+__device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(tmap), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// lane's row of 32 floats -> row `lane` of the warp's staging tile at `sbase` (1024-byte aligned)
+__device__ __forceinline__ void tc_stage_row(uint32_t sbase, int lane, const float (&v)[32]) {
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const uint32_t a = sbase + (uint32_t)lane * 128u + (uint32_t)((c ^ (lane & 7)) << 4);
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v[4 * c]), "f"(v[4 * c + 1]), "f"(v[4 * c + 2]), "f"(v[4 * c + 3]) : "memory");
+  }
+}
+
 // ------------------------------------------------------------------ direct A operand (no apply pass)
 // sample-plane slot of a tile row in the affine table
 __device__ __forceinline__ int tc_sp_index_local(const TcTile& T, bool per_plane, int sample_in_tile, int p) {
@@ -785,7 +804,7 @@ __device__ __forceinline__ void tc_produce_A(const TcConvParams& P, const Geo& g
 template <int BN, int EPI, bool PDL, int EW>
 __device__ __forceinline__ void tc_epilogue(const TcConvParams& P, const Geo& g, const TcTile& T, int n0, int zidx,
                                             uint32_t tmem_base, float* s_bias, uint64_t* bar_acc, uint32_t acc_parity,
-                                            long long* stamp) {
+                                            long long* stamp, uint32_t stage_smem = 0u) {
   constexpr int CSTEP = 32 * (EW / 4);          // column stride between the chunks of one warp
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cfirst = ((warp - 2) >> 2) * 32;    // first chunk of this warp (0 when EW == 4)
@@ -817,6 +836,12 @@ __device__ __forceinline__ void tc_epilogue(const TcConvParams& P, const Geo& g,
   int p = 0, y = 0, x = 0;
   if (EPI == 3 || ((EPI == 1) && P.csum)) tc_decode_fast(T, tok, p, y, x);
   const int pl_stat = p;
+  // bulk-store path: the tile's rows are consecutive rows of the output (always at the large levels; at the small ones
+  // only when a tile is exactly one sample), the operand ring is idle (accumulator complete) and the op has an output map
+  const bool ts = EPI != 2 && stage_smem != 0u && P.tma_store && (!T.small || T.spt == 1);
+  const uint32_t sbase = stage_smem + (uint32_t)(warp - 2) * 4096u;
+  const int ts_row = (int)((size_t)(T.small ? T.b0 : T.b0) * g.L + T.tok0) + q * 32 + (EPI == 0 ? zidx * P.B * g.L : 0);
+  bool ts_pending = false;
 #pragma unroll 1
   for (int c0 = cfirst; c0 < BN; c0 += CSTEP) {
     uint32_t r[32];
@@ -848,8 +873,13 @@ __device__ __forceinline__ void tc_epilogue(const TcConvParams& P, const Geo& g,
       float pv[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) pv[j] = __uint_as_float(r[j]);
+      if (!ts) {
 #pragma unroll
-      for (int j = 0; j < 32; j += 8) st_global_v8(dst + j, pv + j);
+        for (int j = 0; j < 32; j += 8) st_global_v8(dst + j, pv + j);
+      } else {
+        if (ts_pending) { if (lane == 0) tma_store_wait_read(); __syncwarp(); }
+        tc_stage_row(sbase, lane, pv);
+      }
     } else {
       float* dst = P.out + m * P.Cout + n;
       float fv[32];
@@ -884,7 +914,10 @@ __device__ __forceinline__ void tc_epilogue(const TcConvParams& P, const Geo& g,
         fv[j] = v.x; fv[j + 1] = v.y; fv[j + 2] = v.z; fv[j + 3] = v.w;
       }
       if constexpr (EPI != 2) {
-        if (!(P.dbg_skip & 8)) {
+        if (ts) {
+          if (ts_pending) { if (lane == 0) tma_store_wait_read(); __syncwarp(); }
+          tc_stage_row(sbase, lane, fv);
+        } else if (!(P.dbg_skip & 8)) {
 #pragma unroll
           for (int j = 0; j < 32; j += 8) st_global_v8(dst + j, fv + j);
         }
@@ -927,6 +960,12 @@ __device__ __forceinline__ void tc_epilogue(const TcConvParams& P, const Geo& g,
         for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(fv[j]);
       }
     }
+    if (ts) {      // warp-uniform: every row of a bulk-stored tile is live
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) { tma_store_2d(&P.tmOut, sbase, n, ts_row); tma_store_commit(); }
+      ts_pending = true;
+    }
     if ((EPI == 1 || EPI == 3) && P.csum && !(P.dbg_skip & 4)) {
       float fv[32];
 #pragma unroll
@@ -940,6 +979,7 @@ __device__ __forceinline__ void tc_epilogue(const TcConvParams& P, const Geo& g,
       for (int j = 0; j < 32; ++j) rpre[j] = rnext[j];
     }
   }
+  if (ts_pending && lane == 0) tma_store_wait_read();     // the staging tile must outlive the bulk store's reads
 }
 
 // EPI selects the epilogue at compile time (the row-per-lane epilogue is instruction-issue bound, so the
@@ -1144,7 +1184,7 @@ __global__ void __launch_bounds__(DIRECT ? TC_THREADS_DIRECT : TC_THREADS, 1) k_
       const int pw = warp - 2;                    // producer warp 0..7: group = pw >> 2
       tc_produce_A<BN>(P, g, T, it0, it1, it_main, kch, smem0, bar_raw, bar_full, tbl, s_rowinfo, pw >> 2, (pw & 3) * 32 + lane, dbg ? s_pstamp : nullptr);
     }
-    tc_epilogue<BN, EPI, true, 8>(P, g, T, n0, (int)blockIdx.z, tmem_base, s_bias, &bar_acc, 0u, dbg ? s_stamp : nullptr);
+    tc_epilogue<BN, EPI, true, 8>(P, g, T, n0, (int)blockIdx.z, tmem_base, s_bias, &bar_acc, 0u, dbg ? s_stamp : nullptr, smem0);
   }
   if (dbg && threadIdx.x == 64) s_stamp[6] = clock64();              // epilogue stores issued
   tc_fence_before();

@@ -170,9 +170,10 @@ struct MtvHandle_t {
   int64_t weight_bytes = 0;
   // feature bits (MTV_TC_MASK): 0-4 op classes on the tensor-core kernel, 5 split-K, 6 tcgen05 attention, 7 small levels,
   // 8 fused GroupNorm statistics, 9 launch fusions, 10 weight L2 prefetch, 11 L2-persisting small-tensor arena;
-  // 14 consumer GroupNorm + apply fused into small-level split-K reductions, 15 BN = 128 tiles for every split-K-able op;
+  // 14 consumer GroupNorm + apply fused into small-level split-K reductions, 15 BN = 128 tiles for every split-K-able op,
+  // 16 TMA stores of the GEMM epilogue tiles;
   // opt-in (measured slower on B200, kept for A/B — profiles/r01_s2_*.md): 12 persistent chain kernel, 13 direct A operand
-  int tc_mask = 0xcfff;
+  int tc_mask = 0x1cfff;
   cudaStream_t cap_stream = nullptr;
   cudaStream_t capture_stream() {
     if (!cap_stream) CK(cudaStreamCreateWithFlags(&cap_stream, cudaStreamNonBlocking));
@@ -642,6 +643,13 @@ struct Builder {
     op.flops = 2.0 * M * P.Cout * Ktot;
     op.bytes = 4.0 * Ktot * P.Cout + 4.0 * M * Ktot / S.taps + 4.0 * M * P.Cout;
     if (const char* ds = getenv("MTV_TC_DBG_SKIP")) T.dbg_skip = atoi(ds);
+    if (!o.qkv && ((h->tc_mask >> 16) & 1)) {      // epilogue tiles leave through TMA stores (kernels_tc.cu: tma_store_2d)
+      float* dstp = ks > 1 ? T.partial : T.out;
+      const uint64_t dims[2] = {(uint64_t)P.Cout, (uint64_t)(ks > 1 ? ks : 1) * M}; const uint64_t str[1] = {(uint64_t)P.Cout * 4};
+      const uint32_t box[2] = {32, 32};
+      T.tmOut = make_tmap_bf16(dstp, 2, dims, str, box, 128, true);
+      T.tma_store = 1;
+    }
     auto tp = std::make_shared<TcConvParams>(T);
     op.fn = [tp](cudaStream_t s) { return launch_conv_tc(*tp, s); };
     op.tc = tp;

@@ -86,6 +86,8 @@ struct TcConvParams {
   // L2 prefetch of the NEXT tap-GEMM's (HBM-cold) split weights, issued at kernel entry (one slice per CTA)
   const void* pf0; const void* pf1; unsigned long long pf_bytes;
   FusedApply fa;
+  // bulk (TMA) store of the epilogue tile: map of `out` [B*L][Cout] (or of `partial` [ksplit*B*L][Cout]), fp32, box 32 x 32
+  CUtensorMap tmOut; int tma_store;
   int dbg_skip;   // diagnostics only (MTV_TC_DBG_SKIP; results are garbage): 1 no A-tile fetch, 2 no W-tile fetch, 4 no channel sums, 8 no output stores
 };
 constexpr int TC_TABLE_ENTRIES = 3072;   // direct mode: (a, d) pairs per CTA = (sample-plane pairs of the tile) x channels
