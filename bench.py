@@ -34,6 +34,16 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# stdout carries exactly ONE JSON line: libraries that print to fd 1 (NCCL's "NCCL version ..." banner under torchrun) are
+# sent to stderr, and the result line is written to the saved descriptor.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(obj):
+    os.write(_REAL_STDOUT, (json.dumps(obj) + "\n").encode())
+
+
 import torch  # noqa: E402
 
 METRIC = "unet_denoise_steps_per_sec_16f_256px"
@@ -174,7 +184,7 @@ def run_reference_arm(args, rank):
         "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------ GPU arm
@@ -325,7 +335,8 @@ def main():
                 "note": "achieved = algorithmic FLOPs (2*M*N*K, one product = 2 FLOP) of all launches of the family in one forward / "
                         "their summed per-launch time (each launch timed as a node of a private CUDA graph, CUDA events on the "
                         "launching stream); the kernel issues 3 bf16 MMAs per product (split-bf16), so tensor-pipe activity is 3x "
-                        "this fraction; DRAM traffic of sampled launches == algorithmic bytes (profiles/r01_tc_v2_ncu_full.md)"}
+                        "this fraction; traffic = dram__bytes_read+write of the family per launch from the committed ncu list "
+                        "(profiles/r01_s2_launches_b*.md); what paces the main loop: profiles/r01_s2_mainloop_skip.md"}
     else:
         ach = d["mbytes"] / (d["us_per_forward"] * 1e-6) / 1e3  # GB/s
         roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
@@ -368,7 +379,7 @@ def main():
         "kernel_families_us": {k: round(v["us_per_forward"], 1) for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["us_per_forward"])},
         "cpu_baseline": cpu,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
