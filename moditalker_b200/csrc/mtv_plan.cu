@@ -671,10 +671,14 @@ struct Builder {
     for (Op& op : pl->ops) {
       if (!op.tc || op.phase != 1) continue;
       TcConvParams* cur = op.tc.get();
-      if (prev && cur->direct) {          // a direct GEMM has no apply kernel in front of it to do this
+      const unsigned long long wbytes = (unsigned long long)cur->taps * cur->Cin * cur->Cout * 2;
+      // a direct GEMM has no apply kernel in front of it to do this.  Doing it for every weight-heavy GEMM as well (one op more of
+      // lead; MTV_PF_EARLY_MIN = minimum weight bytes) measured slightly slower on B200 (2.14 vs 2.12 ms at B=1): off by default
+      static const long long early_min = [] { const char* e = getenv("MTV_PF_EARLY_MIN"); return e ? atoll(e) : 0ll; }();
+      if (prev && (cur->direct || (early_min > 0 && (long long)(2 * wbytes) >= early_min))) {
         // first K-segment's weights of `cur`: [taps][Cout][Cin] split pair, taken from its W tensor map's base
         auto it = tc_wptr.find(cur);
-        if (it != tc_wptr.end()) { prev->pf0 = it->second.first; prev->pf1 = it->second.second; prev->pf_bytes = (unsigned long long)cur->taps * cur->Cin * cur->Cout * 2; }
+        if (it != tc_wptr.end()) { prev->pf0 = it->second.first; prev->pf1 = it->second.second; prev->pf_bytes = wbytes; }
       }
       prev = cur;
     }
