@@ -636,7 +636,8 @@ struct Builder {
     if (iters >= 16 && ((h->tc_mask >> 5) & 1) && !o.qkv && base * 2 <= h->num_sms + h->num_sms / 4) {
       // spread a fixed amount of shared-memory / weight traffic over (nearly) all SMs; >= 3 K-iterations per CTA (a K-iteration
       // is ~0.5 us at small batch, the extra reduction launch ~4 us: worth it from ~16 iterations up)
-      ks = std::min(iters / 3, std::max(1, h->num_sms / base));
+      static const int min_it = [] { const char* e = getenv("MTV_KS_MIN_ITERS"); return e ? std::max(1, atoi(e)) : 3; }();
+      ks = std::min(iters / min_it, std::max(1, h->num_sms / base));
       ks = std::min(ks, 32);
       while (ks > 1 && (ks - 1) * ((iters + ks - 1) / ks) >= iters) --ks;
     }

@@ -84,3 +84,20 @@ def test_sharded_sampling_gloo_world2(n_chunks):
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), n_chunks, ret), nprocs=world, join=True)
     assert dict(ret) == {0: True, 1: True}
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """bench.py's contract: exactly ONE JSON line on stdout (library chatter goes to stderr), reference arm keys."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--config", "tiny", "--steps", "1",
+                        "--warmup", "0"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "chunk-steps/s" and d["higher_is_better"] is True
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["value"] > 0
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
