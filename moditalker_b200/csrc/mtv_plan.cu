@@ -121,9 +121,6 @@ struct Weight {
 
 struct Tensor {
   float* p = nullptr; int C = 0; int level = 0; double* csum = nullptr; /* [B][3][C][2] per-channel sums, or null */
-  // set when a split-K tensor-core conv at a small level produced this tensor: its reduction kernel can also write the
-  // first simple consumer's normalised operand (FusedApply)
-  std::shared_ptr<mtv::TcConvParams> prod;
 };
 
 struct RunCtx {
@@ -135,9 +132,7 @@ struct Op {
   std::string name; int phase = 1;      // 0 = before graph (reads caller pointers), 1 = graph body, 2 = after
   int launches = 1; double flops = 0, bytes = 0;
   std::function<cudaError_t(cudaStream_t)> fn;
-  // ops the persistent chain kernel can absorb keep their parameter block (see fuse_chains)
-  int ctype = -1;                       // -1: not chainable, CH_APPLY, CH_GEMM (+ its split-K reduction)
-  std::shared_ptr<ApplyParams> ap; std::shared_ptr<TcConvParams> tc;
+  std::shared_ptr<TcConvParams> tc;     // tensor-core tap-GEMMs keep their parameter block (late edits: fused consumer, prefetch)
 };
 
 struct Plan {
@@ -146,7 +141,7 @@ struct Plan {
   std::vector<void*> allocs; size_t alloc_bytes = 0;
   std::map<std::string, Tensor> taps;
   RunCtx ctx;
-  cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr; int runs = 0;
+  cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr; int runs = 0; unsigned long long last_use = 0;
   char* csum_arena = nullptr; size_t csum_cap = 0, csum_used = 0;
   ~Plan() {
     if (exec) cudaGraphExecDestroy(exec);
@@ -166,13 +161,14 @@ struct MtvHandle_t {
   std::unordered_map<const float*, std::pair<void*, void*>> tc_w;   // fp32 conv weight -> split-bf16 pair
   bool dirty = true; bool use_graph = true;
   std::map<int, std::unique_ptr<Plan>> plans;
-  Plan* last_plan = nullptr;
+  Plan* last_plan = nullptr; unsigned long long use_clock = 0;
   int64_t weight_bytes = 0;
   // feature bits (MTV_TC_MASK): 0-4 op classes on the tensor-core kernel, 5 split-K, 6 tcgen05 attention, 7 small levels,
   // 8 fused GroupNorm statistics, 9 launch fusions, 10 weight L2 prefetch, 11 L2-persisting small-tensor arena;
-  // 14 consumer GroupNorm + apply fused into small-level split-K reductions, 15 BN = 128 tiles for every split-K-able op,
-  // 16 TMA stores of the GEMM epilogue tiles;
-  // opt-in (measured slower on B200, kept for A/B — profiles/r01_s2_*.md): 12 persistent chain kernel, 13 direct A operand
+  // 15 BN = 128 tiles for every split-K-able op, 16 TMA stores of the GEMM epilogue tiles.  (Bits 12 / 13 / 14 were the
+  // persistent chain kernel, the direct A operand and the consumer apply fused into the producer behind a grid barrier: all
+  // measured slower on B200 and removed — profiles/r01_s2_chain_experiment.md, r01_s2_direct_experiment.md,
+  // r02_fused_apply_experiment.md.)
   int tc_mask = 0x1cfff;
   cudaStream_t cap_stream = nullptr;
   cudaStream_t capture_stream() {
@@ -193,19 +189,34 @@ struct MtvHandle_t {
     if (small_used + b > small_cap) return nullptr;
     float* p = (float*)(small_arena + small_used); small_used += b; return p;
   }
-  std::map<cudaStream_t, bool> l2_window_set;
-  void apply_l2_window(cudaStream_t s) {
-    if (!small_arena || !small_used || l2_window_set.count(s)) return;
-    static bool limit_set = false;
-    if (!limit_set) { cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, small_cap); limit_set = true; }
+  // The access-policy window is set ONLY on the library's private capture stream (graph kernel nodes inherit it); the
+  // caller's stream is never modified.  The device-wide persisting-L2 limit is raised if needed and restored in mtv_destroy.
+  bool l2_limit_changed = false; size_t l2_limit_prev = 0; size_t l2_window_bytes = 0;
+  void apply_l2_window(cudaStream_t private_stream) {
+    if (!small_arena || !small_used || l2_window_bytes == small_used) return;
+    if (!l2_limit_changed) {
+      size_t prev = 0;
+      if (cudaDeviceGetLimit(&prev, cudaLimitPersistingL2CacheSize) == cudaSuccess && prev < small_cap) {
+        if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, small_cap) == cudaSuccess) { l2_limit_changed = true; l2_limit_prev = prev; }
+        else cudaGetLastError();
+      }
+    }
     cudaStreamAttrValue attr; memset(&attr, 0, sizeof(attr));
     attr.accessPolicyWindow.base_ptr = small_arena;
     attr.accessPolicyWindow.num_bytes = small_used;
     attr.accessPolicyWindow.hitRatio = 1.0f;
     attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
     attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-    if (cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess) cudaGetLastError();
-    l2_window_set[s] = true;
+    if (cudaStreamSetAttribute(private_stream, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess) cudaGetLastError();
+    l2_window_bytes = small_used;
+  }
+  void release_l2_window() {
+    if (l2_limit_changed) {
+      cudaCtxResetPersistingL2Cache();
+      cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, l2_limit_prev);
+      cudaGetLastError();
+      l2_limit_changed = false;
+    }
   }
   int add_weight(const std::string& name, std::vector<int64_t> shape, int kind, float* view = nullptr) {
     Weight w; w.name = name; w.shape = shape; w.kind = kind; w.elems = 1;
@@ -231,6 +242,17 @@ struct MtvHandle_t {
 };
 
 namespace {
+
+// every ABI entry point runs on the handle's device and leaves the caller's current device as it found it
+struct DeviceGuard {
+  int prev = -1; bool switched = false;
+  explicit DeviceGuard(int dev) {
+    CK(cudaGetDevice(&prev));
+    if (prev != dev) { CK(cudaSetDevice(dev)); switched = true; }
+  }
+  ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+  DeviceGuard(const DeviceGuard&) = delete; DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
 
 Geo level_geo(const MtvConfig& c, int level) { return make_geo(c.image_size >> level, (c.image_size / 2) >> level); }
 
@@ -409,8 +431,8 @@ struct Builder {
     n.ref = NormRef{P.nrm_a, P.nrm_d, P.nseg}; n.done = true;
     return n.ref;
   }
-  double* alloc_csum(int C) {
-    const size_t bytes = (size_t)B * 3 * C * 2 * sizeof(double);
+  double* alloc_csum(int C, const Geo& g) {
+    const size_t bytes = csum_elems(g, C, B) * sizeof(double);
     if (pl->csum_used + bytes > pl->csum_cap) throw MtvError("internal: csum arena exhausted");
     double* p = (double*)(pl->csum_arena + pl->csum_used);
     pl->csum_used += bytes;
@@ -445,22 +467,6 @@ struct Builder {
     const int C = S.C0 + S.C1;
     const size_t bytes = (size_t)B * g.L * C * 2;
     SplitBuf out; out.hi = dalloc(bytes); out.lo = dalloc(bytes);
-    // a simple consumer (one source, same geometry, fused statistics) of a small-level split-K conv: the producer's reduction
-    // kernel writes this operand itself (k_tc_splitk_reduce_apply) — no apply launch
-    if (norm_id >= 0 && !raw_out && S.C1 == 0 && S.resample == RS_NONE) {
-      const NormSpec& n = norms[norm_id];
-      TcConvParams* pr = n.x0.prod.get();
-      if (pr && !n.has_x1 && n.x0.p == S.src0 && n.x0.C == C && pr->out == S.src0 && !pr->fa.hi && fuse_gn()) {
-        FusedApply& F = pr->fa;
-        F.gamma = n.gamma; F.beta = n.beta; F.joint = n.joint ? 1 : 0; F.silu = S.silu; F.hi = out.hi; F.lo = out.lo;
-        if (n.film_off >= 0) { F.film = film_buf + n.film_off; F.film_stride = h->arch.J; }
-        if (consumer_w && ((h->tc_mask >> 10) & 1)) {
-          auto it = h->tc_w.find(consumer_w);
-          if (it != h->tc_w.end()) { F.pf0 = it->second.first; F.pf1 = it->second.second; F.pf_bytes = (unsigned long long)S.taps * C * consumer_cout * 2; }
-        }
-        return out;
-      }
-    }
     ApplyParams A{};
     A.src0 = S.src0; A.src1 = S.src1; A.C0 = S.C0; A.C1 = S.C1;
     A.silu = S.silu; A.resample = S.resample; A.B = B; A.geo = g; A.hi = out.hi; A.lo = out.lo;
@@ -494,18 +500,12 @@ struct Builder {
     }
     Op op; op.name = "apply:" + name; op.bytes = (double)B * g.L * C * (raw_out ? 12 : 8);
     op.fn = [A](cudaStream_t s) { return launch_apply_split(A, s); };
-    if (A.csum0 && C <= 2048) { op.ctype = CH_APPLY; op.ap = std::make_shared<ApplyParams>(A); }
     pl->ops.push_back(op);
     return out;
   }
   void make_A_maps(const SplitBuf& buf, int C, int taps, const Geo& g, CUtensorMap* a_hi, CUtensorMap* a_lo) {
     void* ptr[2] = {buf.hi, buf.lo};
     make_A_maps_n(ptr, 2, C, taps, g, a_hi, a_lo, false);
-  }
-  // fp32 maps of ONE raw activation tensor (direct mode): unswizzled 256-byte rows
-  void make_A_maps_f32(const float* src, int C, int taps, const Geo& g, CUtensorMap* dst2) {
-    void* ptr[2] = {(void*)src, nullptr};
-    make_A_maps_n(ptr, 1, C, taps, g, dst2, nullptr, true);
   }
   void make_A_maps_n(void* const* ptr, int n, int C, int taps, const Geo& g, CUtensorMap* a_hi, CUtensorMap* a_lo, bool f32) {
     CUtensorMap* dst[2] = {a_hi, a_lo};
@@ -542,38 +542,9 @@ struct Builder {
       }
     }
   }
-  // ---- direct A operand (kernels_tc.cu: tc_produce_A): the GEMM's producer warps apply GroupNorm / FiLM / SiLU / resample /
-  // concat themselves, so neither the apply launch nor the split-bf16 copy of the activation exists.
-  bool use_direct() const { return h->cfg.kernel_path != 1 && ((h->tc_mask >> 13) & 1); }
-  bool direct_seg_ok(const KSeg& S, int norm_id, const Geo& g) const {
-    if (S.C0 % 64 || S.C1 % 64 || S.resample != RS_NONE) return false;     // resampled sources keep the apply pass
-    if (norm_id < 0) return true;
-    const NormSpec& n = norms[norm_id];
-    const bool small = g.L <= 128;
-    const int spt = small ? std::min(128 / g.L, B) : 1;
-    const int nsp = small ? spt * (n.joint ? 1 : 3) : 1;
-    return (size_t)nsp * (S.C0 + S.C1) <= (size_t)TC_TABLE_ENTRIES;
-  }
-  DirectSeg make_direct_seg(const KSeg& S, int norm_id) {
-    DirectSeg D{};
-    D.src0 = S.src0; D.src1 = S.src1; D.C0 = S.C0; D.C1 = S.C1; D.silu = S.silu; D.resample = S.resample; D.mode = DS_RAW;
-    if (norm_id >= 0) {
-      const NormSpec& n = norms[norm_id];
-      D.gamma = n.gamma; D.beta = n.beta; D.joint = n.joint ? 1 : 0;
-      if (fuse_gn() && n.x0.csum && (!n.has_x1 || n.x1.csum)) {
-        D.mode = DS_NORM_CSUM; D.csum0 = n.x0.csum; D.csum1 = n.has_x1 ? n.x1.csum : nullptr;
-        if (n.film_off >= 0) { D.film = film_buf + n.film_off; D.film_stride = h->arch.J; }
-      } else {
-        const NormRef r = materialize(norm_id);       // FiLM is folded into the tables by k_gn_stats
-        D.mode = DS_NORM_TABLE; D.nrm_a = r.a; D.nrm_d = r.d; D.nrm_nseg = r.nseg;
-      }
-    }
-    return D;
-  }
-
   void conv_tc(const std::string& name, const ConvParams& P, int norm0, int norm1, Tensor* out_t, const TcOpts& o) {
     TcConvParams T{};
-    if (out_t && fuse_gn()) { out_t->csum = alloc_csum(P.Cout); T.csum = out_t->csum; }
+    if (out_t && fuse_gn()) { out_t->csum = alloc_csum(P.Cout, P.geo); T.csum = out_t->csum; }
     if (o.qkv) {
       T.qkv_heads = o.qkv->heads;
       T.q_hi = o.qkv->q_hi; T.q_lo = o.qkv->q_lo; T.k_hi = o.qkv->k_hi; T.k_lo = o.qkv->k_lo;
@@ -595,14 +566,7 @@ struct Builder {
       if (base128 >= 64 || (splittable && ((h->tc_mask >> 15) & 1))) bn = 128;
     }
     T.bn = bn;
-    const bool direct = use_direct() && !o.pre0 && !o.pre1 && !o.raw_out && direct_seg_ok(S, norm0, P.geo) &&
-                        (P.nsegs == 1 || (norm1 < 0 && !P.seg[1].silu && direct_seg_ok(P.seg[1], -1, P.geo)));
-    if (direct) {
-      T.direct = 1;
-      T.dseg[0] = make_direct_seg(S, norm0);
-      make_A_maps_f32(S.src0, S.C0, S.taps, P.geo, T.tmA_hi);
-      if (S.C1) make_A_maps_f32(S.src1, S.C1, S.taps, P.geo, T.tmA_lo);
-    } else {
+    {
       const SplitBuf a0 = o.pre0 ? *o.pre0 : emit_apply(name, S, P.geo, norm0, o.raw_out, S.w, P.Cout);
       make_A_maps(a0, T.Cin, S.taps, P.geo, T.tmA_hi, T.tmA_lo);
     }
@@ -619,14 +583,8 @@ struct Builder {
     if (P.nsegs == 2) {
       const KSeg& X = P.seg[1];
       T.Cin2 = X.C0 + X.C1;
-      if (direct) {
-        T.dseg[1] = make_direct_seg(X, -1);
-        make_A_maps_f32(X.src0, X.C0, 1, P.geo, T.tmA2_hi);
-        if (X.C1) make_A_maps_f32(X.src1, X.C1, 1, P.geo, T.tmA2_lo);
-      } else {
-        const SplitBuf a1 = o.pre1 ? *o.pre1 : emit_apply(name + ".skip", X, P.geo, norm1, nullptr);
-        make_A_maps(a1, T.Cin2, 1, P.geo, T.tmA2_hi, T.tmA2_lo);
-      }
+      const SplitBuf a1 = o.pre1 ? *o.pre1 : emit_apply(name + ".skip", X, P.geo, norm1, nullptr);
+      make_A_maps(a1, T.Cin2, 1, P.geo, T.tmA2_hi, T.tmA2_lo);
       wmaps(X, T.tmW2_hi, T.tmW2_lo);
       Ktot += T.Cin2;
     }
@@ -634,106 +592,32 @@ struct Builder {
     const int base = mtiles * (P.Cout / bn);
     int ks = 1;
     if (iters >= 16 && ((h->tc_mask >> 5) & 1) && !o.qkv && base * 2 <= h->num_sms + h->num_sms / 4) {
-      // spread a fixed amount of shared-memory / weight traffic over (nearly) all SMs; >= 3 K-iterations per CTA (a K-iteration
-      // is ~0.5 us at small batch, the extra reduction launch ~4 us: worth it from ~16 iterations up)
+      // spread a fixed amount of shared-memory / weight traffic over (nearly) all SMs; >= 3 K-iterations per CTA.  The ksplit CTAs
+      // of an output tile wait for each other inside the kernel (tile ticket), so the whole grid must be co-resident: base*ks <= #SMs
       static const int min_it = [] { const char* e = getenv("MTV_KS_MIN_ITERS"); return e ? std::max(1, atoi(e)) : 3; }();
       ks = std::min(iters / min_it, std::max(1, h->num_sms / base));
       ks = std::min(ks, 32);
       while (ks > 1 && (ks - 1) * ((iters + ks - 1) / ks) >= iters) --ks;
     }
     T.ksplit = ks;
-    if (ks > 1) T.partial = (float*)dalloc((size_t)ks * M * P.Cout * sizeof(float));
-    Op op; op.name = "conv_tc:" + name; op.launches = ks > 1 ? 2 : 1;
+    const bool coresident = base * ks <= h->num_sms;
+    if (ks > 1 && !coresident) throw MtvError("internal: split-K grid is not co-resident at " + name);
+    if (ks > 1) T.partial = (float*)dalloc((size_t)base * ks * 128 * bn * sizeof(float));
+    if (ks > 1) T.sync = (unsigned long long*)dalloc((size_t)base * 32 * sizeof(unsigned long long), true);   // kernels_tc.cu: TC_SYNC_STRIDE
+    Op op; op.name = "conv_tc:" + name; op.launches = 1;
     op.flops = 2.0 * M * P.Cout * Ktot;
     op.bytes = 4.0 * Ktot * P.Cout + 4.0 * M * Ktot / S.taps + 4.0 * M * P.Cout;
     if (const char* ds = getenv("MTV_TC_DBG_SKIP")) T.dbg_skip = atoi(ds);
-    if (!o.qkv && ((h->tc_mask >> 16) & 1)) {      // epilogue tiles leave through TMA stores (kernels_tc.cu: tma_store_2d)
-      float* dstp = ks > 1 ? T.partial : T.out;
-      const uint64_t dims[2] = {(uint64_t)P.Cout, (uint64_t)(ks > 1 ? ks : 1) * M}; const uint64_t str[1] = {(uint64_t)P.Cout * 4};
+    if (!o.qkv && ks == 1 && ((h->tc_mask >> 16) & 1)) {      // epilogue tiles leave through TMA stores (kernels_tc.cu: tma_store_2d)
+      const uint64_t dims[2] = {(uint64_t)P.Cout, (uint64_t)M}; const uint64_t str[1] = {(uint64_t)P.Cout * 4};
       const uint32_t box[2] = {32, 32};
-      T.tmOut = make_tmap_bf16(dstp, 2, dims, str, box, 128, true);
+      T.tmOut = make_tmap_bf16(T.out, 2, dims, str, box, 128, true);
       T.tma_store = 1;
     }
     auto tp = std::make_shared<TcConvParams>(T);
     op.fn = [tp](cudaStream_t s) { return launch_conv_tc(*tp, s); };
     op.tc = tp;
-    tc_wptr[tp.get()] = h->tc_w.at(S.w);
-    {
-      const int cpg = P.Cout / 32;
-      const bool groups_fit = (cpg <= 16 && 16 % cpg == 0) || cpg == 32;
-      if (out_t && ks > 1 && P.geo.L <= 128 && !o.qkv && T.csum && groups_fit && ((h->tc_mask >> 14) & 1)) out_t->prod = tp;
-    }
-    if (!direct) op.ctype = CH_GEMM;
     pl->ops.push_back(op);
-  }
-
-  // Weights are HBM-cold every step (529 MB stream through a 126 MB L2).  Each direct-mode tap-GEMM therefore asks L2 for
-  // the NEXT tap-GEMM's weights when it starts (the stand-alone apply kernel used to do this for its consumer).
-  void link_weight_prefetch() {
-    if (!((h->tc_mask >> 10) & 1)) return;
-    TcConvParams* prev = nullptr;
-    for (Op& op : pl->ops) {
-      if (!op.tc || op.phase != 1) continue;
-      TcConvParams* cur = op.tc.get();
-      const unsigned long long wbytes = (unsigned long long)cur->taps * cur->Cin * cur->Cout * 2;
-      // a direct GEMM has no apply kernel in front of it to do this.  Doing it for every weight-heavy GEMM as well (one op more of
-      // lead; MTV_PF_EARLY_MIN = minimum weight bytes) measured slightly slower on B200 (2.14 vs 2.12 ms at B=1): off by default
-      static const long long early_min = [] { const char* e = getenv("MTV_PF_EARLY_MIN"); return e ? atoll(e) : 0ll; }();
-      if (prev && (cur->direct || (early_min > 0 && (long long)(2 * wbytes) >= early_min))) {
-        // first K-segment's weights of `cur`: [taps][Cout][Cin] split pair, taken from its W tensor map's base
-        auto it = tc_wptr.find(cur);
-        if (it != tc_wptr.end()) { prev->pf0 = it->second.first; prev->pf1 = it->second.second; prev->pf_bytes = wbytes; }
-      }
-      prev = cur;
-    }
-  }
-  std::map<const TcConvParams*, std::pair<void*, void*>> tc_wptr;
-
-  // Runs of consecutive chainable graph-body ops become ONE launch of the persistent chain kernel (kernels_tc.cu:
-  // k_chain): kernel boundaries turn into grid-wide barriers, per-kernel prologues are paid once per chain.
-  bool use_chains() const { return h->cfg.kernel_path != 1 && ((h->tc_mask >> 12) & 1); }
-  void fuse_chains() {
-    if (!use_chains()) return;
-    std::vector<Op> out;
-    const int G = h->num_sms;
-    size_t i = 0;
-    while (i < pl->ops.size()) {
-      size_t j = i;
-      while (j < pl->ops.size() && pl->ops[j].phase == 1 && pl->ops[j].ctype >= 0 && !(pl->ops[j].tc && pl->ops[j].tc->fa.hi)) ++j;
-      std::vector<ChainOp> sub;
-      for (size_t k = i; k < j; ++k) {
-        const Op& o = pl->ops[k];
-        ChainOp c; memset(&c, 0, sizeof(c));
-        if (o.ctype == CH_APPLY) {
-          c.type = CH_APPLY; c.apply = *o.ap;
-          // one wave of units: the smallest power-of-two chunk whose unit count fits the grid
-          int chunk = 1;
-          for (;; chunk <<= 1) { c.apply.chunk_tokens = chunk; if (chain_max_grid_units(c) <= G || chunk >= 4096) break; }
-          sub.push_back(c);
-        } else {
-          c.type = CH_GEMM; c.conv = *o.tc; sub.push_back(c);
-          if (o.tc->ksplit > 1) { c.type = CH_REDUCE; sub.push_back(c); }
-        }
-      }
-      if (sub.size() < 2) {                         // nothing to fuse: keep the stand-alone launch(es)
-        for (size_t k = i; k < std::max(j, i + 1); ++k) out.push_back(pl->ops[k]);
-        i = std::max(j, i + 1);
-        continue;
-      }
-      int grid = 1;
-      for (const ChainOp& c : sub) grid = std::max(grid, std::min(G, chain_max_grid_units(c)));
-      ChainLaunch L{};
-      ChainOp* dops = (ChainOp*)dalloc(sub.size() * sizeof(ChainOp));
-      CK(cudaMemcpy(dops, sub.data(), sub.size() * sizeof(ChainOp), cudaMemcpyHostToDevice));
-      L.ops = dops; L.nops = (int)sub.size(); L.counters = (unsigned int*)dalloc(256, true); L.grid = grid;
-      Op op; op.name = "chain:" + pl->ops[i].name.substr(pl->ops[i].name.find(':') + 1) + "+" + std::to_string(sub.size());
-      op.launches = 1;
-      for (size_t k = i; k < j; ++k) { op.flops += pl->ops[k].flops; op.bytes += pl->ops[k].bytes; }
-      op.fn = [L](cudaStream_t s) { return launch_chain(L, s); };
-      out.push_back(op);
-      i = j;
-    }
-    pl->ops.swap(out);
   }
 
   bool fuse_launches() const { return h->cfg.kernel_path != 1 && ((h->tc_mask >> 9) & 1); }
@@ -785,7 +669,7 @@ struct Builder {
       P.bias = h->W(p + ".in_layers.2.bias"); P.out = hmid.p;
       // when both convs run on the tensor cores, conv1's apply kernel also emits the raw split of x that
       // conv2's fused 1x1 skip segment consumes (one launch instead of two)
-      if (r.cin != r.cout && fuse_launches() && !use_direct() && tc_ok_pb(P)) {
+      if (r.cin != r.cout && fuse_launches() && tc_ok_pb(P)) {
         ConvParams P2{}; P2.nsegs = 2; P2.geo = geo(level_out); P2.Cout = r.cout;
         P2.seg[0].C0 = r.cout; P2.seg[0].taps = 9; P2.seg[0].w = h->W(p + ".out_layers.3.weight");
         P2.seg[1].C0 = x0.C; P2.seg[1].C1 = x1 ? x1->C : 0; P2.seg[1].taps = 1; P2.seg[1].w = h->W(p + ".skip_connection.weight");
@@ -961,16 +845,9 @@ struct Builder {
       pl->ops.push_back(op);
     }
     // ---- timestep embedding + every ResBlock's FiLM scale/shift
-    // per-channel statistics arena (zeroed at the start of every forward, inside the graph)
+    // per-channel statistics arena: every slot is rewritten by its producer in every forward (no zeroing, no atomics)
     pl->csum_cap = (size_t)B * (8u << 20);
     pl->csum_arena = (char*)dalloc(pl->csum_cap, true);
-    {
-      Op op; op.name = "zero_csum"; op.launches = 1;
-      op.fn = [plan](cudaStream_t s) {
-        return plan->csum_used ? cudaMemsetAsync(plan->csum_arena, 0, plan->csum_used, s) : cudaSuccess;
-      };
-      pl->ops.push_back(op);
-    }
     film_buf = ((h->tc_mask >> 11) & 1) ? h->small_alloc((size_t)B * A.J * sizeof(float)) : nullptr;
     if (!film_buf) film_buf = (float*)dalloc((size_t)B * A.J * sizeof(float));
     {
@@ -1034,15 +911,26 @@ struct Builder {
   }
 };
 
+// Plans are cached per batch size, at most MTV_MAX_PLANS of them (least recently used is dropped: a caller whose last
+// chunk / batch size varies does not accumulate workspace without bound).  Building a plan allocates its workspace and
+// synchronises the device once (documented in include/mtv_b200.h); steady-state calls never synchronise.
+constexpr size_t MTV_MAX_PLANS = 4;
 Plan* get_plan(MtvHandle_t* h, int B) {
   auto it = h->plans.find(B);
-  if (it != h->plans.end()) return it->second.get();
+  if (it != h->plans.end()) { it->second->last_use = ++h->use_clock; return it->second.get(); }
+  if (h->plans.size() >= MTV_MAX_PLANS) {
+    auto victim = h->plans.begin();
+    for (auto jt = h->plans.begin(); jt != h->plans.end(); ++jt)
+      if (jt->second->last_use < victim->second->last_use) victim = jt;
+    CK(cudaDeviceSynchronize());            // its launches may still be in flight
+    if (h->last_plan == victim->second.get()) h->last_plan = nullptr;
+    h->plans.erase(victim);
+  }
   std::unique_ptr<Plan> pl(new Plan());
+  pl->last_use = ++h->use_clock;
   pl->B = B;
   Builder b(h, pl.get());
   b.build();
-  b.link_weight_prefetch();
-  b.fuse_chains();
   CK(cudaDeviceSynchronize());   // memsets of the statistics scratch
   Plan* raw = pl.get();
   h->plans[B] = std::move(pl);
@@ -1058,11 +946,10 @@ void run_ops(Plan* pl, int phase, cudaStream_t s) {
 }
 
 void forward(MtvHandle_t* h, const RunCtx& ctx, int B, cudaStream_t s) {
-  CK(cudaSetDevice(h->cfg.device));
+  DeviceGuard dg(h->cfg.device);
   ensure_ready(h, s);
   Plan* pl = get_plan(h, B);
   pl->ctx = ctx;
-  h->apply_l2_window(s);
   run_ops(pl, 0, s);
   if (!h->use_graph) {
     run_ops(pl, 1, s);
@@ -1123,7 +1010,7 @@ int mtv_create(const MtvConfig* cfg, MtvHandle* out) {
     int ndev = 0;
     CK(cudaGetDeviceCount(&ndev));
     if (cfg->device < 0 || cfg->device >= ndev) throw MtvError("no such CUDA device");
-    CK(cudaSetDevice(cfg->device));
+    DeviceGuard dg(cfg->device);
     cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, cfg->device));
     if (prop.major != 10)
       throw MtvError(std::string("libmtv_b200 is built for sm_100a only; device is sm_") + std::to_string(prop.major) +
@@ -1134,10 +1021,7 @@ int mtv_create(const MtvConfig* cfg, MtvHandle* out) {
     const char* ng = getenv("MTV_NO_GRAPH");
     h->use_graph = !(ng && ng[0] == '1');
     if (const char* tm = getenv("MTV_TC_MASK")) h->tc_mask = (int)strtol(tm, nullptr, 0);
-    // programmatic dependent launch, by kernel class (mtv_kernels.cuh).  Default: the tensor-core tap-GEMM and the apply
-    // kernels (measured on B200, B=1: none 2.59 ms, GEMM only 2.40, GEMM + apply 2.36, every kernel 2.50 — kernels
-    // pre-launched several deep contend with the running one)
-    { const char* np = getenv("MTV_PDL"); g_mtv_use_pdl = np ? atoi(np) : 5; }
+    // programmatic dependent launch by kernel class: process-wide MTV_PDL mask read once at library load (mtv_kernels.cuh)
     register_weights(h.get());
     *out = h.release();
   });
@@ -1146,9 +1030,10 @@ int mtv_create(const MtvConfig* cfg, MtvHandle* out) {
 int mtv_destroy(MtvHandle h) {
   return guarded([&] {
     if (!h) return;
-    cudaSetDevice(h->cfg.device);
+    DeviceGuard dg(h->cfg.device);
     cudaDeviceSynchronize();
     h->plans.clear();
+    h->release_l2_window();
     if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
     for (void* p : h->allocs) cudaFree(p);
     delete h;
@@ -1160,7 +1045,7 @@ int mtv_load_weight(MtvHandle h, const char* name, const float* data, const int6
   return guarded([&] {
     if (!h || !name || !data) throw MtvError("null argument");
     cudaStream_t s = (cudaStream_t)stream;
-    CK(cudaSetDevice(h->cfg.device));
+    DeviceGuard dg(h->cfg.device);
     const std::string n = strip_prefix(name);
     auto it = h->windex.find(n);
     if (it == h->windex.end()) {
@@ -1219,7 +1104,7 @@ int mtv_ddim_step(MtvHandle h, float* img, const float* eps, const float* noise,
                   float san, float c, float sigma, int32_t last, void* stream) {
   return guarded([&] {
     if (!h || !img || !eps || (!last && !noise)) throw MtvError("null argument");
-    CK(cudaSetDevice(h->cfg.device));
+    DeviceGuard dg(h->cfg.device);
     CK(launch_ddim_step(img, eps, noise, n, sr, srm1, san, c, sigma, last, (cudaStream_t)stream));
   });
 }
@@ -1228,7 +1113,7 @@ int mtv_q_sample(MtvHandle h, const float* x_start, const float* noise, int64_t 
                  void* stream) {
   return guarded([&] {
     if (!h || !x_start || !noise || !out) throw MtvError("null argument");
-    CK(cudaSetDevice(h->cfg.device));
+    DeviceGuard dg(h->cfg.device);
     CK(launch_q_sample(x_start, noise, n, a, b, out, (cudaStream_t)stream));
   });
 }
@@ -1236,7 +1121,7 @@ int mtv_q_sample(MtvHandle h, const float* x_start, const float* noise, int64_t 
 int mtv_plan_info(MtvHandle h, int32_t B, int64_t* n_launches, int64_t* workspace_bytes, int64_t* weight_bytes) {
   return guarded([&] {
     if (!h) throw MtvError("null handle");
-    CK(cudaSetDevice(h->cfg.device));
+    DeviceGuard dg(h->cfg.device);
     Plan* pl = get_plan(h, B);
     int64_t n = 0;
     for (const Op& op : pl->ops) n += op.launches;
@@ -1249,7 +1134,7 @@ int mtv_plan_info(MtvHandle h, int32_t B, int64_t* n_launches, int64_t* workspac
 int mtv_debug_read(MtvHandle h, const char* tag, float* dst, int64_t dst_elems, void* stream) {
   return guarded([&] {
     if (!h || !tag || !dst) throw MtvError("null argument");
-    CK(cudaSetDevice(h->cfg.device));
+    DeviceGuard dg(h->cfg.device);
     Plan* pl = h->last_plan;
     if (!pl) throw MtvError("no forward has run yet");
     auto it = pl->taps.find(tag);
@@ -1264,7 +1149,7 @@ int mtv_debug_read(MtvHandle h, const char* tag, float* dst, int64_t dst_elems, 
 int mtv_debug_tc_timing(MtvHandle h, int64_t* records, int32_t cap, int32_t* count) {
   return guarded([&] {
     if (!h) throw MtvError("null handle");
-    CK(cudaSetDevice(h->cfg.device));
+    DeviceGuard dg(h->cfg.device);
     if (count) { unsigned int n = 0; CK(tc_debug_count(&n)); *count = (int32_t)n; }
     CK(tc_debug_arm((long long*)records, records ? (unsigned int)cap : 0u));
   });
@@ -1276,7 +1161,7 @@ int mtv_profile_forward(MtvHandle h, const float* x, const float* cond, const fl
   return guarded([&] {
     if (!h || !entries || !n) throw MtvError("null argument");
     cudaStream_t s = (cudaStream_t)stream;
-    CK(cudaSetDevice(h->cfg.device));
+    DeviceGuard dg(h->cfg.device);
     ensure_ready(h, s);
     Plan* pl = get_plan(h, B);
     pl->ctx.x = x; pl->ctx.cond = cond; pl->ctx.image_cond = image_cond; pl->ctx.ic_len = image_cond_len;

@@ -12,7 +12,7 @@ struct ApplyParams {
   const float* nrm_a; const float* nrm_d; int nrm_nseg;
   int silu; int resample;                              // RS_*: source geometry relative to `geo`
   // fused-GroupNorm mode (csum0 != nullptr): statistics come from the producers' per-channel sums
-  const double* csum0; const double* csum1;            // [B][3][C0|C1][2]
+  const double* csum0; const double* csum1;            // channel-sum slots of the sources (csum_at), SOURCE geometry
   const float* gamma; const float* beta;               // [C0+C1]
   const float* film; int film_stride;                  // FiLM row b = film + b*stride: scale[C] | shift[C]; nullptr: none
   int joint;                                           // statistics over all three planes (AttentionBlock1D.norm)
@@ -37,29 +37,17 @@ __device__ __forceinline__ void mtv_prefetch_slice(const void* p0, const void* p
   if (p1) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"((const char*)p1 + off), "r"(sz) : "memory");
 }
 
-// "Direct" A operand of one K-segment: instead of a pre-split bf16 tensor fetched by TMA, the GEMM's producer warps read
-// the fp32 activation(s), apply the GroupNorm affine (+FiLM) + SiLU + resample + channel concat themselves and write the
-// split-bf16 tile straight into the swizzled operand ring — the stand-alone apply pass (and its launch) disappears.
-enum { DS_TMA = 0, DS_RAW = 1, DS_NORM_CSUM = 2, DS_NORM_TABLE = 3 };
-struct DirectSeg {
-  const float* src0; const float* src1; int C0, C1;      // sources at the SOURCE geometry (see resample); C0, C1 % 64 == 0
-  const double* csum0; const double* csum1;               // DS_NORM_CSUM: producers' per-channel sums [B][3][C0|C1][2]
-  const float* nrm_a; const float* nrm_d; int nrm_nseg;   // DS_NORM_TABLE: affine tables of k_gn_stats [B][nseg][C]
-  const float* gamma; const float* beta;                  // [C0+C1]
-  const float* film; int film_stride;                     // FiLM row b = film + b*stride: scale[C] | shift[C]; nullptr: none
-  int joint;                                              // statistics over all three planes (AttentionBlock1D.norm)
-  int silu; int resample;                                 // RS_*: source geometry relative to the GEMM's geometry
-  int mode;                                               // DS_*
-};
-
-// Consumer GroupNorm + apply fused into the producer's split-K reduction (k_tc_splitk_reduce_apply): the next op's
-// operand  y = silu?(GN(out) [FiLM]) -> split bf16  is written by the reduction itself.  hi == nullptr: not fused.
-struct FusedApply {
-  const float* gamma; const float* beta; const float* film; int film_stride;
-  int joint; int silu;
-  void* hi; void* lo;                                  // __nv_bfloat16 [B][L][Cout]
-  const void* pf0; const void* pf1; unsigned long long pf_bytes;   // L2 prefetch of the consumer GEMM's weights
-};
+// Per-channel GroupNorm sums without atomics (order-deterministic): a producing tap-GEMM CTA leaves the (sum, sum of
+// squares) of its rows of channel c in ONE slot per (sample, plane, row block), consumers add the slots in index order.
+//   L > 128 : slot = 128-token tile within the plane (xy: res*res/128 slots; yt, xt: t*res/128)
+//   L <= 128: one slot per (sample, plane)
+// Layout: double [B][3][CSUM_NS(geo)][C][2].
+__host__ __device__ inline int csum_ns(const Geo& g) { return g.L > 128 ? (g.res * g.res) / 128 : 1; }
+__host__ __device__ inline int csum_nslots(const Geo& g, int p) { return g.L > 128 ? (p == 0 ? g.res * g.res : g.t * g.res) / 128 : 1; }
+__host__ __device__ inline size_t csum_at(const Geo& g, int C, int b, int p, int slot, int c) {
+  return ((((size_t)b * 3 + p) * csum_ns(g) + slot) * C + c) * 2;
+}
+__host__ __device__ inline size_t csum_elems(const Geo& g, int C, int B) { return (size_t)B * 3 * csum_ns(g) * C * 2; }
 
 // D[B*L][Cout] = sum_tap A_tap[B*L][Cin] * W[tap][Cout][Cin]^T   (+bias, +residual)
 struct TcConvParams {
@@ -76,21 +64,21 @@ struct TcConvParams {
   int taps, Cin, Cout, B; Geo geo;
   const float* bias; const float* resid; int resid_mode;
   float* out; float* partial; int ksplit;
-  double* csum;                       // optional [B][3][Cout][2]: per-channel sums of `out` for the next GroupNorm
+  double* csum;                       // optional channel-sum slots of `out` (csum_at) for the next GroupNorm
+  // split-K tickets (64-bit generation counters, never reset, zero once at allocation): word [tile * 32] belongs to output
+  // tile `tile` = blockIdx.x * gridDim.y + blockIdx.y.  Required by ksplit > 1, which the host only selects for grids of at
+  // most #SMs CTAs (every CTA of the launch is co-resident, so the in-kernel wait cannot deadlock).
+  unsigned long long* sync;
   // qkv mode (qkv_heads > 0): instead of fp32 `out`, the epilogue writes the attention operands directly —
   // split-bf16 Q (pre-scaled by log2(e)/sqrt(D)) and K as [B*H][L][D], V^T as [B*H][D][L]  (see k_qkv_split)
   int qkv_heads;
   void* q_hi; void* q_lo; void* k_hi; void* k_lo; void* vt_hi; void* vt_lo;
-  // direct mode (direct != 0): the A operands of BOTH K-segments are produced in-kernel (tmA_* unused)
-  int direct; DirectSeg dseg[2];
   // L2 prefetch of the NEXT tap-GEMM's (HBM-cold) split weights, issued at kernel entry (one slice per CTA)
   const void* pf0; const void* pf1; unsigned long long pf_bytes;
-  FusedApply fa;
   // bulk (TMA) store of the epilogue tile: map of `out` [B*L][Cout] (or of `partial` [ksplit*B*L][Cout]), fp32, box 32 x 32
   CUtensorMap tmOut; int tma_store;
   int dbg_skip;   // diagnostics only (MTV_TC_DBG_SKIP; results are garbage): 1 no A-tile fetch, 2 no W-tile fetch, 4 no channel sums, 8 no output stores
 };
-constexpr int TC_TABLE_ENTRIES = 3072;   // direct mode: (a, d) pairs per CTA = (sample-plane pairs of the tile) x channels
 
 // qkv fp32 [B][L][3C] -> split-bf16 Q (pre-scaled), K [B*H][L][D] and V^T [B*H][D][L]
 struct QkvSplitParams {
@@ -111,19 +99,6 @@ struct AttnTcParams {
 };
 cudaError_t launch_qkv_split(const QkvSplitParams& P, cudaStream_t s);
 cudaError_t launch_attn_tc(const AttnTcParams& P, cudaStream_t s);
-
-// Persistent chain kernel: a run of consecutive {apply, tap-GEMM, split-K reduction} launches executed by ONE
-// cooperative-style grid (<= one CTA per SM, all co-resident) with a grid-wide barrier between sub-ops instead of a
-// kernel boundary.  At small batch the forward is bound by launch gaps and per-kernel prologues, not by work.
-enum { CH_APPLY = 0, CH_GEMM = 1, CH_REDUCE = 2 };
-struct ChainOp {               // device-resident array element (tensor maps live in global memory)
-  int type; int pad_[15];
-  TcConvParams conv;           // CH_GEMM, CH_REDUCE
-  ApplyParams apply;           // CH_APPLY (fused-GroupNorm mode only)
-};
-struct ChainLaunch { const ChainOp* ops; int nops; unsigned int* counters /* [2], zero, self-resetting */; int grid; };
-cudaError_t launch_chain(const ChainLaunch& L, cudaStream_t s);
-int         chain_max_grid_units(const ChainOp& op);   // work units of one sub-op (host-side, for sizing the grid)
 
 cudaError_t launch_apply_split(const ApplyParams& P, cudaStream_t s);
 cudaError_t launch_repack_split_w(const float* src, void* hi, void* lo, int Cout, int Cin, int taps, cudaStream_t s);

@@ -38,25 +38,30 @@ torch.cuda.synchronize()
 _lib.check(lib.mtv_debug_tc_timing(h, None, 0, ctypes.byref(cnt)), "disarm")
 n = min(cnt.value, cap)
 rec = buf.cpu().view(cap, 16)[:n]
-rec = rec[(rec[:, 0] >> 62) == 0]          # chain-kernel records (scripts/chain_timing.py) carry bit 62
-prec = rec[(rec[:, 0] >> 61) == 1]         # direct-mode producer stamps
-rec = rec[(rec[:, 0] >> 61) == 0]
 print(f"{n} CTA records in one forward (B={B})")
+# record: [0] grid, [1] shape, [2..9] clock64 stamps: entry, setup done, first operands, last operands, accumulator
+# complete, split-K tile ticket passed | arrival at the grid barrier, grid barrier passed, epilogue done; [10],[11] globaltimer
 groups = defaultdict(list)
 for r in rec.tolist():
-    groups[(r[0], r[1])].append(r)
+    groups[(r[0], r[1], r[15])].append(r)
 rows = []
-for (g0, g1), rs in groups.items():
+for (g0, g1, fl), rs in groups.items():
     gx, gy, gz = g0 & 0xffff, (g0 >> 16) & 0xffff, (g0 >> 32) & 0xffff
     iters, taps, cin, cout = g1 & 0xffff, (g1 >> 16) & 0xff, (g1 >> 24) & 0xffff, (g1 >> 40) & 0xffff
     def mean(f):
         return sum(f(r) for r in rs) / len(rs)
-    setup = mean(lambda r: r[3] - r[2]); first = mean(lambda r: r[5] - r[3]); stream = mean(lambda r: r[6] - r[5])
-    drain = mean(lambda r: r[7] - r[6]); epi = mean(lambda r: r[8] - r[7]); total = mean(lambda r: r[9] - r[2])
+    def mx(f):
+        return max(f(r) for r in rs)
+    setup = mean(lambda r: r[3] - r[2]); first = mean(lambda r: r[4] - r[3]); stream = mean(lambda r: r[5] - r[4])
+    drain = mean(lambda r: r[6] - r[5])
+    t5 = lambda r: r[7] if r[7] else r[6]
+    t6 = lambda r: r[8] if r[8] else t5(r)
+    e1 = mean(lambda r: t5(r) - r[6]); e2 = mean(lambda r: t6(r) - t5(r)); e3 = mean(lambda r: r[9] - t6(r))
+    total = mean(lambda r: r[14] - r[2])
     span = mean(lambda r: r[11] - r[10])
     launches = len(rs) / max(1, gx * gy * gz)
-    rows.append((total * launches, f"grid {gx:3d}x{gy:2d}x{gz:2d} iters {iters:3d} taps {taps} Cin {cin:4d} Cout {cout:4d} | launches {launches:5.1f} | "
-                 f"setup {setup:6.0f} first {first:6.0f} stream {stream:6.0f} drain {drain:6.0f} epi {epi:6.0f} total {total:7.0f} cyc | span {span / 1e3:6.2f} us"))
+    rows.append((total * launches, f"grid {gx:3d}x{gy:2d}x{gz:2d} iters {iters:3d} taps {taps} Cin {cin:4d} Cout {cout:4d} fa {fl & 1} | launches {launches:5.1f} | "
+                 f"setup {setup:6.0f} first {first:6.0f} stream {stream:6.0f} drain {drain:6.0f} | tail: to-ticket/arrive {e1:6.0f} barrier {e2:6.0f} finish {e3:6.0f} | total {total:7.0f} cyc | span {span / 1e3:6.2f} us"))
 for _, line in sorted(rows, reverse=True):
     print(line)
 
@@ -83,20 +88,3 @@ for i, L in enumerate(launches):
     prev_end = L["t1"]
 print(f"sum of TC launch durations {tot_dur:.1f} us; span {(launches[-1]['t1'] - t_base) / 1e3:.1f} us")
 
-# ---- direct-mode producer phases (group 0, thread 0): per iteration slot: wait for the ring slot, produce, fence+arrive
-if len(prec):
-    pg = defaultdict(list)
-    for r in prec.tolist():
-        pg[(r[0] & ~(1 << 61), r[1])].append(r)
-    print("\ndirect-mode producer phases, cycles (mean over CTAs): [start-of-iteration since kernel entry | wait | produce | fence+arrive] x first 3 iterations of group 0")
-    for (g0, g1), rs in pg.items():
-        gx, gy, gz = g0 & 0xffff, (g0 >> 16) & 0xffff, (g0 >> 32) & 0xffff
-        iters, taps, cin, cout = g1 & 0xffff, (g1 >> 16) & 0xff, (g1 >> 24) & 0xffff, (g1 >> 40) & 0xffff
-        out = []
-        for j in range(3):
-            ok = [r for r in rs if r[3 + 4 * j + 3] > 0]
-            if not ok:
-                continue
-            m = lambda f: sum(f(r) for r in ok) / len(ok)
-            out.append(f"[{m(lambda r: r[3 + 4 * j] - r[2]):7.0f} | {m(lambda r: r[4 + 4 * j] - r[3 + 4 * j]):6.0f} | {m(lambda r: r[5 + 4 * j] - r[4 + 4 * j]):6.0f} | {m(lambda r: r[6 + 4 * j] - r[5 + 4 * j]):5.0f}]")
-        print(f"grid {gx:3d}x{gy:2d}x{gz:2d} iters {iters:3d} taps {taps} Cin {cin:4d} Cout {cout:4d} n={len(rs):4d}  " + " ".join(out))

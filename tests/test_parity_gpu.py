@@ -152,17 +152,14 @@ def test_eager_capture_replay_are_bit_identical():
 
 
 def test_launch_modes_do_not_change_results(monkeypatch):
-    """Programmatic dependent launch (any class mask), the launch fusions and the persistent chain kernel (kernel
-    boundaries replaced by grid barriers) only reorder / overlap work: outputs must be bit-identical to the plain
-    serial plan."""
+    """Programmatic dependent launch (any class mask) and graph capture only reorder / overlap work: outputs must
+    be bit-identical to the plain serial plan.  (GroupNorm sums and split-K reductions run in a fixed order — per-CTA
+    slots, no atomics — so this is a guarantee, not luck.)"""
     cfg = config_by_name("tiny")
     x, cond, ic, t = synth_inputs(2, seed=88, t=[5, 900])
     outs = {}
     for name, env in (("pdl default", {}), ("pdl off", {"MTV_PDL": "0"}), ("pdl all", {"MTV_PDL": "31"}),
-                      ("no graph", {"MTV_NO_GRAPH": "1"}),
-                      # opt-in paths = default feature mask (0xcfff) + their bit: same tiles, same summation order
-                      ("chain kernel", {"MTV_TC_MASK": "0xdfff"}), ("chain kernel, pdl off", {"MTV_TC_MASK": "0xdfff", "MTV_PDL": "0"}),
-                      ("direct A operand", {"MTV_TC_MASK": "0xefff"})):
+                      ("no graph", {"MTV_NO_GRAPH": "1"})):
         for k in ("MTV_PDL", "MTV_NO_GRAPH", "MTV_TC_MASK"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
