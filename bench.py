@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — denoising-step throughput of the MToV hot path on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload step|config3] [--config base|longvid]
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
 
 Step      one pass of the hot path over one batch: UNet epsilon-prediction
@@ -12,14 +12,21 @@ Step      one pass of the hot path over one batch: UNet epsilon-prediction
 value     chunk-steps/s over all ranks, inputs resident in HBM, CUDA-event timed,
           max over ranks; weak scaling (each rank samples its own chunks, one
           all-gather of the final latents inside the timed region when N>1).
-e2e       same metric through the public nn.Module API with HOST (pinned) buffers:
-          every step copies x/cond/image_cond/t host->device, runs the UNet forward and
-          the DDIM update, and reads the updated latent back device->host (sync per step).
-roofline  dominant kernel family of one forward, CUDA events around each launch.
+e2e       the same metric through the public sampler: wall clock (CUDA events around
+          host-visible work) of ``DDPM.sample()`` — the call MToV/sample.py:377 makes — for the
+          50-step config, conditioning copied host(pinned)->device, final latent read device->host.
+roofline  dominant kernel family of one forward, CUDA events around each launch; whole-step
+          DRAM traffic from the committed ncu capture (profiles/r02_traffic.json).
+gpu_eager_baseline
+          the reference's OWN modules (staged by oracle/build_ref.py under oracle/_ref, else the
+          oracle port moved to the GPU) in eager PyTorch fp32 on the same B200: the honest GPU baseline.
 cpu_baseline / --impl reference
           the CPU restatement of the reference path (oracle/unet_oracle.py; the
           reference tree itself cannot travel to the GPU box and has no installable
           package) on all host threads, bounded sample.
+--workload config3
+          BASELINE.json configs[2]: 64 frames = 4 chunks, 100-step schedule, chunks sharded over the
+          ranks by ``sample_chunks_sharded`` (one all-gather); at most 4-way parallel by construction.
 """
 from __future__ import annotations
 
@@ -59,8 +66,11 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--chunks-per-gpu", type=int, default=1)
     ap.add_argument("--config", default="base", choices=["base", "longvid", "tiny"])
+    ap.add_argument("--workload", default="step", choices=["step", "config3"])
+    ap.add_argument("--chunks", type=int, default=4, help="config3: total number of 16-frame chunks (64 frames = 4)")
     ap.add_argument("--cpu-baseline-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-eager-baseline", action="store_true")
     return ap.parse_args()
 
 
@@ -187,6 +197,135 @@ def run_reference_arm(args, rank):
     emit(line)
 
 
+# ------------------------------------------------------------------------------ reference eager on the GPU
+def _staged_reference():
+    """(UNetModel, DiffusionWrapper, DDPM, ViTAutoencoder | None) of the reference itself, staged under oracle/_ref."""
+    from oracle import build_ref
+    p = build_ref.staged_path()
+    if p is None:
+        return None
+    if p not in sys.path:
+        sys.path.insert(0, p)
+    from models.ddpm.unet import DiffusionWrapper as RW, UNetModel as RU      # noqa: E402
+    from losses.ddpm import DDPM as RD                                        # noqa: E402
+    try:
+        from models.autoencoder.autoencoder_vit import ViTAutoencoder as RA   # noqa: E402
+    except Exception:
+        RA = None
+    return RU, RW, RD, RA
+
+
+def gpu_eager_baseline(cfg_name, dev, batches, steps=20, warmup=5):
+    """The reference UNet (+ its own DDIM loop) in eager PyTorch fp32 on `dev`.  allow_tf32 flags are left at
+    PyTorch's defaults (cudnn.allow_tf32 = True: cuDNN convs may use TF32; matmul.allow_tf32 = False) — i.e. the
+    reference as a user runs it; both flags are recorded."""
+    from moditalker_b200.synth import synth_inputs, synth_state_dict
+    cfg = cfg_by_name(cfg_name)
+    out = {"dtype": "f32", "allow_tf32": {"cudnn": bool(torch.backends.cudnn.allow_tf32), "matmul": bool(torch.backends.cuda.matmul.allow_tf32)},
+           "steps": steps, "warmup": warmup, "by_batch": {}}
+    ref = _staged_reference()
+    if ref is not None:
+        RU, RW, RD, RA = ref
+        model = RW(RU(**cfg))
+        model.load_state_dict(synth_state_dict(cfg, 0, "diffusion_model."), strict=True)
+        model = model.to(dev).eval()
+        out["kind"] = "reference"
+        out["what"] = ("unmodified MToV/models/ddpm/unet.py + losses/ddpm.py (staged by oracle/build_ref.py), eager PyTorch on the same GPU: "
+                       "DDPM.ddim_sample loop body = DiffusionWrapper.forward + the reference's own update ops")
+        for B in batches:
+            ddpm = RD(model, channels=4, image_size=32, sampling_timesteps=steps, w=0.0).to(dev)
+            _, cond, ic, _ = synth_inputs(B, seed=2)
+            cond, ic = cond.to(dev), ic.to(dev)
+            wd = RD(model, channels=4, image_size=32, sampling_timesteps=max(warmup, 2), w=0.0).to(dev)
+            with torch.no_grad():
+                wd.sample(batch_size=B, cond=cond, image_cond=ic)             # warm-up: cuDNN autotune / lazy init
+                torch.cuda.synchronize(dev)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                ddpm.sample(batch_size=B, cond=cond, image_cond=ic)           # `steps` iterations of the reference loop
+                e1.record()
+                torch.cuda.synchronize(dev)
+            ms = e0.elapsed_time(e1) / steps
+            out["by_batch"][str(B)] = {"ms_per_step": ms, "value": B / (ms * 1e-3), "unit": UNIT}
+        del model
+    else:
+        from oracle.unet_oracle import Oracle
+        orc = Oracle(cfg, synth_state_dict(cfg, 0), device=dev)
+        out["kind"] = "port"
+        out["what"] = "oracle restatement of the reference forward (same ATen ops) moved to the GPU; oracle/_ref not staged on this box"
+        for B in batches:
+            x, cond, ic, _ = synth_inputs(B, seed=2)
+            x, cond, ic = x.to(dev), cond.to(dev), ic.to(dev)
+            t = torch.full((B,), 500, device=dev, dtype=torch.long)
+            with torch.no_grad():
+                for _ in range(warmup):
+                    orc.forward(x, cond, ic, t)
+                torch.cuda.synchronize(dev)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(steps):
+                    orc.forward(x, cond, ic, t)
+                e1.record()
+                torch.cuda.synchronize(dev)
+            ms = e0.elapsed_time(e1) / steps
+            out["by_batch"][str(B)] = {"ms_per_step": ms, "value": B / (ms * 1e-3), "unit": UNIT}
+    torch.cuda.empty_cache()
+    return out
+
+
+def eager_autoencoder_times(dev):
+    """SURVEY §8(f)1 context: the reference ViTAutoencoder (stays reference PyTorch) timed in eager mode on this GPU next to the
+    sampling loop: extract() x4 + decode_from_sample() per 16-frame chunk (sample.py:328-332, 385)."""
+    ref = _staged_reference()
+    if ref is None or ref[3] is None:
+        return None
+    RA = ref[3]
+    dd = {"double_z": False, "channels": 384, "resolution": 256, "timesteps": 16, "skip": 1, "in_channels": 3, "out_ch": 3,
+          "num_res_blocks": 2, "attn_resolutions": [], "splits": 1}
+    try:
+        torch.manual_seed(0)
+        ae = RA(4, dd).to(dev).eval()
+        x = torch.rand(1, 3, 16, 256, 256, device=dev) * 2 - 1
+        res = {}
+        with torch.no_grad():
+            for name, fn in (("extract", lambda: ae.extract(x)), ("decode_from_sample", None)):
+                if name == "decode_from_sample":
+                    z = ae.extract(x)
+                    fn = lambda: ae.decode_from_sample(z)
+                for _ in range(2):
+                    fn()
+                torch.cuda.synchronize(dev)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(5):
+                    fn()
+                e1.record()
+                torch.cuda.synchronize(dev)
+                res[name + "_ms"] = e0.elapsed_time(e1) / 5
+        res["per_chunk_ms"] = 4 * res["extract_ms"] + res["decode_from_sample_ms"]
+        res["what"] = "reference ViTAutoencoder (62 M params, random init), eager fp32, one 16-frame 256x256 chunk: 4 x extract + 1 x decode per chunk"
+        del ae
+        torch.cuda.empty_cache()
+        return res
+    except Exception as e:      # context only: never fail the bench line for it
+        return {"error": repr(e)[:200]}
+
+
+def _chunk_noise_fn(chunk_ids):
+    """noise_fn for DDPM: every draw is a stack of per-chunk tensors seeded by (chunk id, draw index), so a chunk sees the same
+    noise whatever rank / local batch it lands in (sharding must be invisible in the output)."""
+    state = {"n": 0}
+
+    def fn(kind, shape, device):
+        k = state["n"]; state["n"] += 1
+        outs = []
+        for c in chunk_ids:
+            g = torch.Generator().manual_seed(1000003 * int(c) + k)
+            outs.append(torch.randn(tuple(shape[1:]), generator=g))
+        return torch.stack(outs).to(device)
+    return fn
+
+
 # ------------------------------------------------------------------------------ GPU arm
 def main():
     args = parse()
@@ -208,38 +347,49 @@ def main():
         __graft_entry__.build()          # no-op when the in-tree .so is current
     if world > 1:
         dist.barrier()
-    from moditalker_b200 import DDPM, DiffusionWrapper, UNetModel, _lib
+    from moditalker_b200 import DDPM, DiffusionWrapper, UNetModel, _lib, chunk_partition, sample_chunks_sharded
     from moditalker_b200.synth import synth_inputs, synth_state_dict
 
     cfg = cfg_by_name(args.config)
-    B = args.chunks_per_gpu
     model = DiffusionWrapper(UNetModel(**cfg))
     model.load_state_dict(synth_state_dict(cfg, 0, "diffusion_model."), strict=True)
     model = model.to(dev).eval()
+    if args.workload == "config3":
+        run_config3(args, rank, world, dev, model)
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    B = args.chunks_per_gpu
     ddpm = DDPM(model, channels=4, image_size=32, sampling_timesteps=SAMPLING_STEPS, w=0.0).to(dev)
     # each rank samples its own chunks (weak scaling): inputs depend on the global chunk index
-    x_h, cond_h, ic_h, _ = synth_inputs(B * world, seed=2)
+    x_all, cond_all, ic_all, _ = synth_inputs(B * world, seed=2)
     sl = slice(rank * B, (rank + 1) * B)
-    x_h, cond_h, ic_h = x_h[sl].contiguous().pin_memory(), cond_h[sl].contiguous().pin_memory(), ic_h[sl].contiguous().pin_memory()
+    x_h, cond_h, ic_h = x_all[sl].contiguous().pin_memory(), cond_all[sl].contiguous().pin_memory(), ic_all[sl].contiguous().pin_memory()
     cond, ic = cond_h.to(dev), ic_h.to(dev)
     pairs = ddpm.time_pairs()
     lib, h = model.diffusion_model.native_handle(dev)
     stream = torch.cuda.current_stream(dev)
     tconds = {t: torch.full((B,), t, device=dev, dtype=torch.long) for t, _ in pairs}
-    img = x_h.to(dev).clone()
     W, K = max(args.warmup, 3), max(args.steps, 1)
 
-    def dev_step(i):
-        time_, tn = pairs[i % (len(pairs) - 1)]      # never the final (noise-free) pair: every step is a full update
-        eps = model(img, cond, ic, tconds[time_])
-        noise = torch.randn_like(img)
-        sr, srm1, san, c, sigma = ddpm.step_scalars(time_, tn)
-        _lib.check(lib.mtv_ddim_step(h, img.data_ptr(), eps.data_ptr(), noise.data_ptr(), img.numel(), sr, srm1, san, c,
-                                     sigma, 0, stream.cuda_stream), "mtv_ddim_step")
+    # the per-step noise is a fixed tensor per GLOBAL chunk (seeded by the chunk id) so that at N > 1 rank 0 can recompute a
+    # foreign chunk and check the gathered latents (gather_check); generated once, outside the timed region
+    def chunk_noise(ids):
+        return torch.stack([torch.randn((4, 2048), generator=torch.Generator().manual_seed(77000 + int(c))) for c in ids]).to(dev)
+    noise = chunk_noise(range(rank * B, (rank + 1) * B))
 
+    def run_steps(img_, cond_, ic_, noise_, tc_, n0, n):
+        for i in range(n0, n0 + n):
+            time_, tn = pairs[i % (len(pairs) - 1)]      # never the final (noise-free) pair: every step is a full update
+            eps = model(img_, cond_, ic_, tc_[time_])
+            sr, srm1, san, c, sigma = ddpm.step_scalars(time_, tn)
+            _lib.check(lib.mtv_ddim_step(h, img_.data_ptr(), eps.data_ptr(), noise_.data_ptr(), img_.numel(), sr, srm1, san, c,
+                                         sigma, 0, stream.cuda_stream), "mtv_ddim_step")
+
+    img = x_h.to(dev).clone()
     with torch.no_grad():
-        for i in range(W):
-            dev_step(i)
+        run_steps(img, cond, ic, noise, tconds, 0, W)
         torch.cuda.synchronize()
         gathered = torch.empty((world * B, 4, 2048), device=dev) if world > 1 else None
         if world > 1:
@@ -249,8 +399,7 @@ def main():
         clk = ClockSampler(local_rank) if rank == 0 else None
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        for i in range(K):
-            dev_step(W + i)
+        run_steps(img, cond, ic, noise, tconds, W, K)
         if world > 1:
             dist.all_gather_into_tensor(gathered, img)     # the path's single collective (final latents)
         e1.record(stream)
@@ -263,40 +412,47 @@ def main():
         ms_total = float(ms.item())
         clocks = clk.stop() if clk else None
 
-        # ---- e2e: host buffers in, host result out, every step
-        eps_h = torch.empty((B, 4, 2048), dtype=torch.float32).pin_memory()
-        t_h = torch.full((B,), 500, dtype=torch.long).pin_memory()
-        x_d, c_d, ic_d, t_d = torch.empty_like(img), torch.empty_like(cond), torch.empty_like(ic), torch.empty((B,), device=dev, dtype=torch.long)
+        # ---- gather_check (N > 1): rank 0 recomputes the first chunk of the LAST rank alone and compares it with the gathered row
+        gather_check = None
+        if world > 1 and rank == 0:
+            gid = (world - 1) * B
+            xs = x_all[gid:gid + 1].to(dev).clone()
+            cs, ics = cond_all[gid:gid + 1].to(dev), ic_all[gid:gid + 1].to(dev)
+            t1 = {t: torch.full((1,), t, device=dev, dtype=torch.long) for t, _ in pairs}
+            run_steps(xs, cs, ics, chunk_noise([gid]), t1, 0, W + K)
+            torch.cuda.synchronize()
+            err = float((gathered[gid:gid + 1].double() - xs.double()).norm() / xs.double().norm().clamp_min(1e-30))
+            gather_check = {"chunk": gid, "from_rank": world - 1, "rel_l2": err, "tol": 1e-4, "ok": bool(err <= 1e-4),
+                            "what": "gathered latent of a foreign chunk vs a single-GPU recompute of that chunk on rank 0 (same per-chunk noise)"}
 
-        def e2e_step(i):
-            time_, tn = pairs[i % (len(pairs) - 1)]
-            t_h.fill_(time_)
-            x_d.copy_(x_h, non_blocking=True); c_d.copy_(cond_h, non_blocking=True)
-            ic_d.copy_(ic_h, non_blocking=True); t_d.copy_(t_h, non_blocking=True)
-            eps = model(x_d, c_d, ic_d, t_d)
-            noise = torch.randn_like(x_d)
-            sr, srm1, san, c, sigma = ddpm.step_scalars(time_, tn)
-            _lib.check(lib.mtv_ddim_step(h, x_d.data_ptr(), eps.data_ptr(), noise.data_ptr(), x_d.numel(), sr, srm1, san, c,
-                                         sigma, 0, stream.cuda_stream), "mtv_ddim_step")
-            eps_h.copy_(x_d, non_blocking=True)           # the step's result: the updated latent x_{t-1}
-            stream.synchronize()                          # the caller reads it on the host
+        # ---- e2e: the public sampler, host conditioning in, host latent out
+        n_samples = max(2, (K + SAMPLING_STEPS - 1) // SAMPLING_STEPS)
+        z_h = torch.empty((B, 4, 2048), dtype=torch.float32).pin_memory()
+        c_d, ic_d = torch.empty_like(cond), torch.empty_like(ic)
 
-        for i in range(3):
-            e2e_step(i)
+        def e2e_sample():
+            c_d.copy_(cond_h, non_blocking=True); ic_d.copy_(ic_h, non_blocking=True)
+            z = ddpm.sample(batch_size=B, cond=c_d, image_cond=ic_d)
+            z_h.copy_(z, non_blocking=True)
+            stream.synchronize()                          # the caller reads z on the host
+        e2e_sample()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
+        t0 = time.perf_counter()
         e0.record(stream)
-        for i in range(K):
-            e2e_step(i)
+        for _ in range(n_samples):
+            e2e_sample()
         e1.record(stream)
         torch.cuda.synchronize()
-        ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        wall_ms = 1e3 * (time.perf_counter() - t0)
+        ms2 = torch.tensor([max(e0.elapsed_time(e1), wall_ms)], device=dev)
         if world > 1:
             dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
         e2e_ms = float(ms2.item())
-        h2d = x_h.numel() * 4 + cond_h.numel() * 4 + ic_h.numel() * 4 + t_h.numel() * 8
-        d2h = eps_h.numel() * 4
+        e2e_steps = n_samples * SAMPLING_STEPS
+        h2d = (cond_h.numel() + ic_h.numel()) * 4
+        d2h = z_h.numel() * 4
 
         # ---- per-kernel-family timing of one forward (events around every launch, same stream)
         fam = {}
@@ -324,10 +480,10 @@ def main():
     pk = peaks()
     info = model.diffusion_model.plan_info(B)
     value = world * B * K / (ms_total / 1e3)
-    e2e_value = world * B * K / (e2e_ms / 1e3)
+    e2e_value = world * B * e2e_steps / (e2e_ms / 1e3)
     dom = max((k for k in fam if k not in ("copy_t", "copy_out", "pack_in")), key=lambda k: fam[k]["us_per_forward"])
     d = fam[dom]
-    if dom in ("conv", "attn", "conv_tc", "attn_tc"):
+    if dom in ("conv", "attn", "conv_tc", "attn_tc", "attn_fused"):
         ach = d["gflop"] / (d["us_per_forward"] * 1e-6) / 1e3   # TFLOP/s
         # the family is timed launch by launch, each replayed back to back on its own: the BURST peak is the denominator
         roof = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
@@ -337,29 +493,51 @@ def main():
                         "their summed per-launch time (each launch timed as a node of a private CUDA graph, CUDA events on the "
                         "launching stream); the kernel issues 3 bf16 MMAs per product (split-bf16), so tensor-pipe activity is 3x "
                         "this fraction; traffic = dram__bytes_read+write of the family per launch from the committed ncu list "
-                        "(profiles/r01_s2_launches_b*.md); what paces the main loop: profiles/r01_s2_mainloop_skip.md"}
+                        "(profiles/r02_launches_b*.md)"}
     else:
         ach = d["mbytes"] / (d["us_per_forward"] * 1e-6) / 1e3  # GB/s
         roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
                 "frac": ach / pk["hbm_gbs"], "traffic": None, "peak_source": f"{pk['source']} (MEASURED_PEAKS.json hbm_gbs)"}
     roof["us_per_forward"] = d["us_per_forward"]
     roof["launches_per_forward"] = d["launch_groups"]
-    # DRAM traffic of the same kernel family from the committed ncu capture (profiles/r01_traffic.json, written by
-    # scripts/summarize_traffic.py from `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum`); per launch like `achieved`
-    tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if os.path.exists(tp):
-        tr = json.load(open(tp)).get(f"B{B}", {}).get(dom)
-        if tr:
-            roof["traffic"] = tr["dram_bytes"] / max(1, tr["launches"])
-            roof["traffic_per_forward"] = tr["dram_bytes"]
-            roof["algorithmic_bytes_per_forward"] = d["mbytes"] * 1e6
     # whole-step HBM view (0.54 GB algorithmic bytes per step at B=1)
     step_bytes = info["weight_bytes"] + B * (10.6e6 + 0.14e6)
+    roof["step_algorithmic_bytes"] = step_bytes
     roof["step_hbm_frac"] = (step_bytes / ((ms_total / K) * 1e-3)) / 1e9 / pk["hbm_gbs"]
+    # DRAM traffic from the committed ncu capture (profiles/r02_traffic.json, written by scripts/summarize_traffic.py from
+    # `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum`): per launch of the dominant family like `achieved`, and summed
+    # over EVERY kernel of one step (step_traffic) against the step's algorithmic bytes
+    for tp in ("r02_traffic.json", "r01_traffic.json"):
+        tp = os.path.join(ROOT, "profiles", tp)
+        if os.path.exists(tp) and args.config == "base":
+            tj = json.load(open(tp)).get(f"B{B}", {})
+            tr = tj.get(dom)
+            if tr:
+                roof["traffic"] = tr["dram_bytes"] / max(1, tr["launches"])
+                roof["traffic_per_forward"] = tr["dram_bytes"]
+                roof["algorithmic_bytes_per_forward"] = d["mbytes"] * 1e6
+            if "_step" in tj:
+                roof["step_traffic"] = tj["_step"]["dram_bytes"]
+                roof["step_traffic_over_algorithmic"] = tj["_step"]["dram_bytes"] / step_bytes
+                roof["step_traffic_source"] = tj["_step"].get("how", os.path.basename(tp))
+            break
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         cpu = cpu_reference_steps(args.config, args.cpu_baseline_steps, B)
+    eager = None
+    ae = None
+    if not args.no_eager_baseline and world == 1:
+        try:
+            eager = gpu_eager_baseline(args.config, dev, sorted({B, 8} if B == 1 else {B}))
+            eb = eager["by_batch"].get(str(B))
+            if eb:
+                eager.update(value=eb["value"], ms_per_step=eb["ms_per_step"], unit=UNIT, batch=B,
+                             speedup_device=value / eb["value"], speedup_e2e=e2e_value / eb["value"])
+            if args.config == "base" and B == 1:
+                ae = eager_autoencoder_times(dev)
+        except Exception as e:
+            eager = {"error": repr(e)[:300]}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
@@ -374,16 +552,99 @@ def main():
             "parallelism": f"chunk-sharded x{world}" + (", one all-gather of final latents in the timed region" if world > 1 else ""),
         },
         "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": e2e_ms / K, "api": "DiffusionWrapper.forward + DDIM update, pinned host buffers in, updated latent out, sync per step"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d / SAMPLING_STEPS, "d2h_bytes_per_step": d2h / SAMPLING_STEPS,
+                "ms_per_step": e2e_ms / e2e_steps, "samples": n_samples, "ms_per_sample": e2e_ms / n_samples,
+                "frames_per_sec": 16.0 * world * B * n_samples / (e2e_ms / 1e3),
+                "api": "DDPM.sample(batch_size, cond, image_cond) — the call MToV/sample.py:377 makes — 50-step DDIM from pure noise: pinned host "
+                       "cond/image_cond copied to the device, torch.randn start + per-step torch.randn_like noise (as the reference), final latent "
+                       "copied to pinned host memory, stream synchronised per sample; wall clock / (samples * 50 steps); h2d/d2h bytes are per-sample "
+                       "totals divided by 50"},
         "gpu_launches": int(K * (info["launches"] + 1)),
+        "launches_per_forward": int(info["launches"]),
         "roofline": roof,
         "kernel_families_us": {k: round(v["us_per_forward"], 1) for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["us_per_forward"])},
+        "gpu_eager_baseline": eager,
+        "autoencoder_eager": ae,
         "cpu_baseline": cpu,
     }
+    if gather_check is not None:
+        line["gather_check"] = gather_check
     emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_config3(args, rank, world, dev, model):
+    """BASELINE.json configs[2]: '100-step DDPM sample, 64 frames, frame-batch sharded across the GPUs with an NCCL gather' =
+    DDPM(sampling_timesteps=100).sample over 4 chunks through sample_chunks_sharded (the '100-step DDPM' path is the
+    DDIM sampler with eta=1).  Strong scaling with a hard ceiling of `chunks`-way parallelism."""
+    import torch.distributed as dist
+    from moditalker_b200 import DDPM, chunk_partition, sample_chunks_sharded
+    from moditalker_b200.synth import synth_inputs
+    S = 100
+    n = args.chunks
+    _, cond, ic, _ = synth_inputs(n, seed=2)
+    cond_h, ic_h = cond.pin_memory(), ic.pin_memory()
+    mine = chunk_partition(n, world, rank)
+
+    def one_run():
+        ddpm = DDPM(model, channels=4, image_size=32, sampling_timesteps=S, w=0.0).to(dev)
+        ddpm.noise_fn = _chunk_noise_fn(mine)
+        c_d, i_d = cond_h.to(dev, non_blocking=True), ic_h.to(dev, non_blocking=True)
+        z = sample_chunks_sharded(lambda c, i, ns: ddpm.sample(batch_size=c.shape[0], cond=c, image_cond=i), c_d, i_d)
+        return z
+
+    with torch.no_grad():
+        # warm-up: a short schedule with the same batch shape (plan build + graph capture)
+        wd = DDPM(model, channels=4, image_size=32, sampling_timesteps=4, w=0.0).to(dev)
+        if mine:
+            idx = torch.tensor(mine)
+            wd.sample(batch_size=len(mine), cond=cond[idx].to(dev), image_cond=ic[idx].to(dev))
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        clk = ClockSampler(dev.index) if rank == 0 else None
+        stream = torch.cuda.current_stream(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record(stream)
+        z = one_run()
+        z_h = z.cpu() if z is not None else None
+        e1.record(stream)
+        torch.cuda.synchronize()
+        wall = 1e3 * (time.perf_counter() - t0)
+        ms = torch.tensor([max(e0.elapsed_time(e1), wall)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        ms_total = float(ms.item())
+        clocks = clk.stop() if clk else None
+        gather_check = None
+        if rank == 0 and world > 1:
+            gid = n - 1                       # a chunk sampled on another rank (chunk c -> rank c mod W)
+            ddpm = DDPM(model, channels=4, image_size=32, sampling_timesteps=S, w=0.0).to(dev)
+            ddpm.noise_fn = _chunk_noise_fn([gid])
+            zr = ddpm.sample(batch_size=1, cond=cond[gid:gid + 1].to(dev), image_cond=ic[gid:gid + 1].to(dev)).cpu()
+            err = float((z_h[gid:gid + 1].double() - zr.double()).norm() / zr.double().norm().clamp_min(1e-30))
+            gather_check = {"chunk": gid, "from_rank": gid % world, "rel_l2": err, "tol": 1e-4, "ok": bool(err <= 1e-4)}
+    if rank != 0:
+        return
+    value = n * S / (ms_total / 1e3)
+    info = model.diffusion_model.plan_info(max(1, len(mine)))
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": S, "warmup": 4, "ms_per_step": ms_total / S,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"BASELINE.json configs[2]: MToV 100-step sample (DDIM eta=1), {16 * n} frames = {n} chunks, {args.config}.yaml, chunks sharded "
+                               f"over {world} GPU(s) by sample_chunks_sharded (chunk c -> rank c mod W, one all-gather of final latents)",
+                   "chunks": n, "chunks_on_rank0": len(mine), "parallel_ceiling": f"{n}-way: a chunk cannot be split across GPUs (24 joint attentions per step)",
+                   "frames_per_sec": 16.0 * n / (ms_total / 1e3), "seconds_per_clip": ms_total / 1e3},
+        "clocks": clocks,
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": (cond_h.numel() + ic_h.numel()) * 4 / S, "d2h_bytes_per_step": n * 4 * 2048 * 4 / S,
+                "api": "sample_chunks_sharded(DDPM.sample) end to end: pinned host conditioning in, gathered latents on the host out, wall clock"},
+        "gpu_launches": int(S * (info["launches"] + 1)),
+    }
+    if gather_check is not None:
+        line["gather_check"] = gather_check
+    emit(line)
 
 
 if __name__ == "__main__":

@@ -32,7 +32,7 @@ def timestep_embedding(t: torch.Tensor, dim: int, dtype) -> torch.Tensor:
     f_i = exp(-ln(1e4) i / half); frequencies are built in fp32 like the
     reference, then promoted."""
     half = dim // 2
-    freqs = torch.exp(-math.log(10000) * torch.arange(0, half, dtype=torch.float32) / half)
+    freqs = torch.exp(-math.log(10000) * torch.arange(0, half, dtype=torch.float32) / half).to(t.device)
     args = t[:, None].float() * freqs[None]
     emb = torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
     return emb.to(dtype)
@@ -58,11 +58,14 @@ def qkv_attention_legacy(qkv: torch.Tensor, n_heads: int) -> torch.Tensor:
 
 
 class Oracle:
-    def __init__(self, config: dict, state_dict: Dict[str, torch.Tensor], dtype=torch.float32):
+    def __init__(self, config: dict, state_dict: Dict[str, torch.Tensor], dtype=torch.float32, device="cpu"):
+        """``device`` is "cpu" for the oracle proper; bench.py's gpu_eager_baseline fallback moves the same ATen ops to the
+        GPU when the staged reference (oracle/_ref) is absent."""
         self.arch: UNetArch = build_arch(**config)
         strip = "diffusion_model."
         self.dtype = dtype
-        self.p = {(k[len(strip):] if k.startswith(strip) else k): v.detach().to("cpu", dtype)
+        self.device = torch.device(device)
+        self.p = {(k[len(strip):] if k.startswith(strip) else k): v.detach().to(self.device, dtype)
                   for k, v in state_dict.items()}
         self.taps: Dict[str, torch.Tensor] = {}   # optional intermediate captures
         self.capture: Optional[set] = None
@@ -138,7 +141,7 @@ class Oracle:
         emb = F.linear(emb, *self._w("time_embed.0"))
         emb = F.linear(F.silu(emb), *self._w("time_embed.2"))
         # unet.py:1022-1025: image_cond keeps its xy plane, yt/xt are zero-filled
-        ic = torch.cat([image_cond[:, :, :1024], torch.zeros(B, cond.shape[1] // 2, 1024, dtype=dt)], dim=2)
+        ic = torch.cat([image_cond[:, :, :1024], torch.zeros(B, cond.shape[1] // 2, 1024, dtype=dt, device=x.device)], dim=2)
         h = torch.cat([x, cond, ic], dim=1)
         planes = [
             h[:, :, 0:1024].reshape(B, -1, 32, 32),
