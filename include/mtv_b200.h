@@ -115,8 +115,6 @@ int  mtv_debug_read(MtvHandle h, const char* tag, float* dst, int64_t dst_elems,
  * tap-GEMM.  While armed every CTA appends one 16 x int64 record to the DEVICE buffer `records`
  * (capacity `cap` records).  *count receives the number of records written since the previous call. */
 int  mtv_debug_tc_timing(MtvHandle h, int64_t* records, int32_t cap, int32_t* count);
-/* diagnostics: clusters of `nqb` fused-attention CTAs (head dim D) that can be resident at once on the current device */
-int  mtv_debug_max_clusters(int32_t D, int32_t nqb);
 
 /* Per-kernel timing of one forward (CUDA events around every launch, serialised):
  * fills up to `cap` entries of (name, microseconds); returns the count in *n. */

@@ -57,7 +57,6 @@ _SIGNATURES = {
     "mtv_plan_info": (c_int32, [c_void_p, c_int32, POINTER(c_int64), POINTER(c_int64), POINTER(c_int64)]),
     "mtv_debug_read": (c_int32, [c_void_p, c_char_p, c_void_p, c_int64, c_void_p]),
     "mtv_debug_tc_timing": (c_int32, [c_void_p, c_void_p, c_int32, POINTER(c_int32)]),
-    "mtv_debug_max_clusters": (c_int32, [c_int32, c_int32]),
     "mtv_profile_forward": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int32, c_void_p,
                                       POINTER(MtvKernelTime), c_int32, POINTER(c_int32), c_void_p]),
 }

@@ -213,212 +213,10 @@ struct AttnSmem {
   static constexpr int P_SLOT = AT_BQ * 128;               // P tile: 128 rows x 64 keys bf16 (only when P goes through smem)
   static constexpr int TOTAL = 2 * Q_SLOT + AT_NS * STAGE + (AT_P_IN_TMEM ? 0 : 2 * P_SLOT) + 1024;
   static constexpr int STAGE_TX = 2 * K_BYTES + 2 * V_BYTES;
-  // fused front end (qkv projection of this CTA's tokens): two stages of {A_hi, A_lo 128 x 64 bf16 | W_hi, W_lo 3D x 64 bf16},
-  // aliased over the attention buffers (the front end is finished before the first Q / K / V tile is requested), followed by the
-  // GroupNorm affine table a[C] | d[C] (C <= 1024)
-  static constexpr int FE_A = AT_BQ * 128;
-  static constexpr int FE_W = align_up(3 * D * 128);
-  static constexpr int FE_STAGE = 2 * FE_A + 2 * FE_W;
-  static constexpr int FE_NS = 2;
-  static constexpr int FE_RING = FE_NS * FE_STAGE;
-  static constexpr int FE_AFF_OFF = (FE_RING > TOTAL - 1024 ? FE_RING : TOTAL - 1024);
-  static constexpr int TOTAL_FUSED = FE_AFF_OFF + 2 * 1024 * 4 + 1024;
 };
 
-
-// ------------------------------------------------------------------ fused front end: GroupNorm + qkv projection
-__device__ __forceinline__ uint64_t a_desc_sw128(uint32_t smem_addr) { return a_desc(smem_addr, 128); }
-__device__ __forceinline__ void a_tmem_ld8_nowait(uint32_t taddr, uint32_t (&r)[8]) { a_tmem_ld8(taddr, r); }
-__device__ __forceinline__ void a_cluster_sync() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void a_split2(float y0, float y1, uint32_t& hi, uint32_t& lo) {
-  hi = cvt_bf16x2(y0, y1);
-  lo = cvt_bf16x2(y0 - __uint_as_float(hi << 16), y1 - __uint_as_float(hi & 0xffff0000u));
-}
-
-// All 320 threads.  warp 0: TMA of the head's qkv weight rows; warp 1: MMA issuer; warps 2-9: statistics -> affine table,
-// A-operand producers (x fp32 -> GroupNorm -> split bf16 in the UMMA 128B-swizzled K-major layout), then the epilogue
-// (TMEM -> +bias, Q pre-scaled -> Q / K / V^T split bf16 in global memory).  Ends with a cluster barrier: the K / V rows written by
-// the other query tiles of this (sample, head) are visible to the TMA loads that follow.
 template <int D>
-__device__ __forceinline__ void attn_front_end(const AttnTcParams& P, uint8_t* ring, uint32_t smem0, uint32_t tmem_base, int bh, int sg,
-                                               int t_lo, int len, int q0, uint64_t* fe_full, uint64_t* fe_empty, uint64_t* fe_done,
-                                               double* s_stat /* [64] */) {
-  using SM = AttnSmem<D>;
-  constexpr int N3 = 3 * D;
-  constexpr uint32_t IDESC_FE = a_idesc(AT_BQ, N3);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = bh / P.heads, h = bh - b * P.heads;
-  const int C = P.C, kch = C / 64;
-  const int nrow = min(AT_BQ, len - q0);
-  float* s_aff = reinterpret_cast<float*>(ring + SM::FE_AFF_OFF);
-  if (warp == 0) {
-    // =============================== weights: rows [h*3D, (h+1)*3D) of the (3C x C) qkv matrix ===============================
-    int stage = 0; uint32_t phase = 0;
-    for (int kc = 0; kc < kch; ++kc) {
-      if (kc >= SM::FE_NS) a_mbar_wait(&fe_empty[stage], phase ^ 1u);
-      if (a_elect_one()) {
-        a_mbar_expect_tx(&fe_full[stage], 2 * N3 * 128);
-        const uint32_t sW_hi = smem0 + stage * SM::FE_STAGE + 2 * SM::FE_A, sW_lo = sW_hi + SM::FE_W;
-        a_tma_2d(sW_hi, &P.tmWq_hi, a_smem_u32(&fe_full[stage]), kc * 64, h * N3);
-        a_tma_2d(sW_lo, &P.tmWq_lo, a_smem_u32(&fe_full[stage]), kc * 64, h * N3);
-      }
-      __syncwarp();
-      if (++stage == SM::FE_NS) { stage = 0; phase ^= 1u; }
-    }
-  } else if (warp == 1) {
-    // =============================== MMA issuer ===============================
-    const uint64_t d0 = a_desc_sw128(smem0);
-    int stage = 0; uint32_t phase = 0;
-    for (int kc = 0; kc < kch; ++kc) {
-      a_mbar_wait(&fe_full[stage], phase);
-      a_fence_after();
-      const uint64_t dA = d0 + (uint64_t)((uint32_t)(stage * SM::FE_STAGE) >> 4);
-      if (a_elect_one()) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint64_t a_hi = dA + (uint64_t)(k * 2), a_lo = a_hi + (uint64_t)(SM::FE_A >> 4);
-          const uint64_t w_hi = a_hi + (uint64_t)((2 * SM::FE_A) >> 4), w_lo = w_hi + (uint64_t)(SM::FE_W >> 4);
-          a_mma(tmem_base, a_hi, w_hi, IDESC_FE, (kc | k) ? 1u : 0u);
-          a_mma(tmem_base, a_lo, w_hi, IDESC_FE, 1u);
-          a_mma(tmem_base, a_hi, w_lo, IDESC_FE, 1u);
-        }
-        a_commit(&fe_empty[stage]);
-      }
-      __syncwarp();
-      if (++stage == SM::FE_NS) { stage = 0; phase ^= 1u; }
-    }
-    if (a_elect_one()) a_commit(fe_done);
-    __syncwarp();
-  } else {
-    const int et = threadIdx.x - 64;
-    // =============================== GroupNorm statistics -> a[C] | d[C] ===============================
-    {
-      const int cpg = C / 32;
-      const int grp = et >> 3, l8 = et & 7;
-      const int p = P.nseg == 3 ? sg : 0;
-      double s, ss;
-      const CsumSrc CS{P.fe_csum, nullptr, C, 0};
-      csum_group_sum(CS, P.fe_geo, b, p, P.fe_joint != 0, grp, cpg, l8, 8, s, ss);
-#pragma unroll
-      for (int off = 4; off > 0; off >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, off); ss += __shfl_xor_sync(0xffffffffu, ss, off); }
-      if (l8 == 0) {
-        const Geo& g = P.fe_geo;
-        const double cnt = (double)cpg * (P.fe_joint ? (double)g.L : (double)(p == 0 ? g.res * g.res : g.t * g.res));
-        const double mean = s / cnt;
-        double var = ss / cnt - mean * mean; var = var < 0.0 ? 0.0 : var;
-        s_stat[2 * grp] = mean; s_stat[2 * grp + 1] = rsqrt(var + 1e-5);
-      }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      for (int c = et; c < C; c += 256) {
-        const int gq = c / cpg;
-        const double a = s_stat[2 * gq + 1] * (double)__ldg(P.fe_gamma + c);
-        const double d = (double)__ldg(P.fe_beta + c) - s_stat[2 * gq] * a;
-        s_aff[c] = (float)a; s_aff[C + c] = (float)d;
-      }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-    }
-    // =============================== A operand producers ===============================
-    // thread -> (row r = et / 2, channel half = et & 1): 32 consecutive channels (128 bytes) of its row per 64-channel chunk
-    {
-      const int r = et >> 1, half = et & 1;
-      const bool rlive = r < nrow;
-      const float* xrow = P.fe_x + ((size_t)b * P.L + t_lo + q0 + (rlive ? r : 0)) * C + half * 32;
-      float4 cur[8];
-      auto fetch = [&](int kc, float4 (&v)[8]) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = rlive ? __ldg(reinterpret_cast<const float4*>(xrow + kc * 64) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-      };
-      fetch(0, cur);
-      int stage = 0; uint32_t phase = 0;
-      for (int kc = 0; kc < kch; ++kc) {
-        float4 nxt[8];
-        if (kc + 1 < kch) fetch(kc + 1, nxt);
-        if (kc >= SM::FE_NS) a_mbar_wait(&fe_empty[stage], phase ^ 1u);
-        const uint32_t sA_hi = smem0 + stage * SM::FE_STAGE, sA_lo = sA_hi + SM::FE_A;
-        const float* ta = s_aff + kc * 64 + half * 32;
-#pragma unroll
-        for (int j4 = 0; j4 < 4; ++j4) {           // one 16-byte chunk (8 channels) of hi and of lo per trip
-          uint32_t hi[4], lo[4];
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const float4 v = cur[2 * j4 + e];
-            const float4 a = *reinterpret_cast<const float4*>(ta + 8 * j4 + 4 * e), d = *reinterpret_cast<const float4*>(ta + C + 8 * j4 + 4 * e);
-            float y0 = fmaf(v.x, a.x, d.x), y1 = fmaf(v.y, a.y, d.y), y2 = fmaf(v.z, a.z, d.z), y3 = fmaf(v.w, a.w, d.w);
-            if (!rlive) { y0 = y1 = y2 = y3 = 0.f; }
-            a_split2(y0, y1, hi[2 * e], lo[2 * e]); a_split2(y2, y3, hi[2 * e + 1], lo[2 * e + 1]);
-          }
-          const uint32_t off = (uint32_t)r * 128u + (uint32_t)((((half << 2) | j4) ^ (r & 7)) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sA_hi + off), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sA_lo + off), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA (async proxy)
-        __syncwarp();
-        if (lane == 0) a_mbar_arrive(&fe_full[stage]);
-        if (kc + 1 < kch) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) cur[j] = nxt[j];
-        }
-        if (++stage == SM::FE_NS) { stage = 0; phase ^= 1u; }
-      }
-    }
-    // =============================== epilogue: Q / K / V^T of this CTA's rows ===============================
-    {
-      a_mbar_wait(fe_done, 0);
-      a_fence_after();
-      const int half = (warp - 2) >> 2, qq = warp & 3;
-      const int row = qq * 32 + lane;
-      const bool live = row < nrow;
-      const int tok = t_lo + q0 + row;
-      const uint32_t lane_addr = (uint32_t)(qq * 32) << 16;
-      const float qs = 1.4426950408889634f * rsqrtf((float)D);    // both D^-1/4 factors and log2(e), folded into Q
-      constexpr int UH = N3 / 16;                                  // 8-column units per warp half
-#pragma unroll
-      for (int u = 0; u < UH; ++u) {
-        const int c = (half * UH + u) * 8;                         // column within the head's 3D: q [0,D) k [D,2D) v [2D,3D)
-        uint32_t rr[8];
-        a_tmem_ld8(tmem_base + lane_addr + (uint32_t)c, rr);
-        a_tmem_wait_ld();
-        const int kind = c / D, d0 = c - kind * D;
-        const float4 b0 = __ldg(reinterpret_cast<const float4*>(P.fe_bias + h * N3 + c)), b1 = __ldg(reinterpret_cast<const float4*>(P.fe_bias + h * N3 + c + 4));
-        float v[8] = {__uint_as_float(rr[0]) + b0.x, __uint_as_float(rr[1]) + b0.y, __uint_as_float(rr[2]) + b0.z, __uint_as_float(rr[3]) + b0.w,
-                      __uint_as_float(rr[4]) + b1.x, __uint_as_float(rr[5]) + b1.y, __uint_as_float(rr[6]) + b1.z, __uint_as_float(rr[7]) + b1.w};
-        if (kind == 0) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] *= qs;
-        }
-        __align__(16) __nv_bfloat16 hh[8], ll[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { hh[i] = __float2bfloat16_rn(v[i]); ll[i] = __float2bfloat16_rn(v[i] - __bfloat162float(hh[i])); }
-        if (live) {
-          if (kind < 2) {
-            __nv_bfloat16* ph = reinterpret_cast<__nv_bfloat16*>(kind == 0 ? P.q_hi : P.k_hi) + ((size_t)bh * P.L + tok) * D + d0;
-            __nv_bfloat16* pw = reinterpret_cast<__nv_bfloat16*>(kind == 0 ? P.q_lo : P.k_lo) + ((size_t)bh * P.L + tok) * D + d0;
-            *reinterpret_cast<uint4*>(ph) = *reinterpret_cast<const uint4*>(hh);
-            *reinterpret_cast<uint4*>(pw) = *reinterpret_cast<const uint4*>(ll);
-          } else {
-            __nv_bfloat16* ph = reinterpret_cast<__nv_bfloat16*>(P.vt_hi) + ((size_t)bh * D + d0) * P.L + tok;
-            __nv_bfloat16* pw = reinterpret_cast<__nv_bfloat16*>(P.vt_lo) + ((size_t)bh * D + d0) * P.L + tok;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) { ph[(size_t)i * P.L] = hh[i]; pw[(size_t)i * P.L] = ll[i]; }
-          }
-        }
-      }
-    }
-  }
-  // every query tile of this (sample, head) has written its K / V rows: release them to the cluster, generic -> async proxy
-  a_fence_before();
-  asm volatile("fence.proxy.async;" ::: "memory");
-  __syncwarp();
-  a_cluster_sync();
-  asm volatile("fence.proxy.async;" ::: "memory");
-  a_fence_after();
-}
-
-template <int D, bool FUSED>
-__global__ void __launch_bounds__(AT_THREADS, (D <= 32 && !FUSED) ? 2 : 1) k_attn_tc(const __grid_constant__ AttnTcParams P) {
+__global__ void __launch_bounds__(AT_THREADS, (D <= 32) ? 2 : 1) k_attn_tc(const __grid_constant__ AttnTcParams P) {
   using SM = AttnSmem<D>;
   mtv_prefetch_slice(P.pf0, P.pf1, P.pf_bytes, blockIdx.x + gridDim.x * blockIdx.y, gridDim.x * gridDim.y);
   constexpr uint32_t IDESC_S = a_idesc(AT_BQ, AT_BKV);
@@ -429,8 +227,6 @@ __global__ void __launch_bounds__(AT_THREADS, (D <= 32 && !FUSED) ? 2 : 1) k_att
   __shared__ __align__(8) uint64_t bar_q, bar_full[AT_NS], bar_empty[AT_NS], bar_s_full, bar_s_free, bar_p_full, bar_o_full;
   __shared__ uint32_t tmem_base_s;
   __shared__ float s_xchg[2][2][AT_BQ];   // [block parity][half][row]: row max (and the final row sum) exchange
-  __shared__ __align__(8) uint64_t fe_full[FUSED ? SM::FE_NS : 1], fe_empty[FUSED ? SM::FE_NS : 1], fe_done;
-  __shared__ double s_stat[FUSED ? 64 : 1];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem0 = (a_smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -456,10 +252,6 @@ __global__ void __launch_bounds__(AT_THREADS, (D <= 32 && !FUSED) ? 2 : 1) k_att
     a_mbar_init(&bar_s_full, 1); a_mbar_init(&bar_o_full, 1);
     // one arrival per softmax WARP (8), not per thread: 256 same-address mbarrier arrivals per key block serialise in shared memory
     a_mbar_init(&bar_s_free, 8); a_mbar_init(&bar_p_full, 8);
-    if (FUSED) {
-      for (int s = 0; s < SM::FE_NS; ++s) { a_mbar_init(&fe_full[s], 9); a_mbar_init(&fe_empty[s], 1); }   // 8 producer warps + the TMA's expect_tx
-      a_mbar_init(&fe_done, 1);
-    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -473,9 +265,7 @@ __global__ void __launch_bounds__(AT_THREADS, (D <= 32 && !FUSED) ? 2 : 1) k_att
   const uint32_t tmem_base = tmem_base_s;
   const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 64;
   const uint32_t tmem_Phi = tmem_base + 128, tmem_Plo = tmem_base + 160;
-  MTV_PDL_WAIT();        // Q / K / V^T (or, fused: x and its channel sums) are written by the preceding kernel
-  if constexpr (FUSED)
-    attn_front_end<D>(P, smem_raw + (smem0 - a_smem_u32(smem_raw)), smem0, tmem_base, bh, sg, t_lo, len, q0, fe_full, fe_empty, &fe_done, s_stat);
+  MTV_PDL_WAIT();        // Q / K / V^T are written by the preceding k_qkv_split
 
   if (warp == 0) {
     // =============================== TMA producer ===============================
@@ -738,54 +528,13 @@ __global__ void __launch_bounds__(AT_THREADS, (D <= 32 && !FUSED) ? 2 : 1) k_att
 template <int D>
 static cudaError_t launch_attn_tc_d(const AttnTcParams& P, cudaStream_t s) {
   using SM = AttnSmem<D>;
+  cudaError_t e = cudaFuncSetAttribute(k_attn_tc<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL);
+  if (e != cudaSuccess) return e;
   int nqb = 0;
   for (int i = 0; i < P.nseg; ++i) nqb += (P.seg_off[i + 1] - P.seg_off[i] + AT_BQ - 1) / AT_BQ;
   dim3 grid(nqb, P.B * P.heads);
-  if (!P.fe_x) {
-    cudaError_t e = cudaFuncSetAttribute(k_attn_tc<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL);
-    if (e != cudaSuccess) return e;
-    { cudaError_t le_ = launch_kc(PDL_CLASS_ATTN_TC, k_attn_tc<D, false>, dim3(grid), dim3(AT_THREADS), (size_t)(SM::TOTAL), s, P); if (le_ != cudaSuccess) return le_; }
-    return cudaGetLastError();
-  }
-  // fused front end: the query tiles of one (sample, head) are one cluster (<= 16 CTAs: non-portable size)
-  if (nqb > 16 || P.C > 1024 || P.C % 64) return cudaErrorInvalidValue;
-  cudaError_t e = cudaFuncSetAttribute(k_attn_tc<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL_FUSED);
-  if (e != cudaSuccess) return e;
-  if (nqb > 8) {
-    e = cudaFuncSetAttribute(k_attn_tc<D, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-    if (e != cudaSuccess) return e;
-  }
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = grid; cfg.blockDim = dim3(AT_THREADS); cfg.dynamicSmemBytes = SM::TOTAL_FUSED; cfg.stream = s;
-  cudaLaunchAttribute at[2];
-  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[0].val.programmaticStreamSerializationAllowed = mtv_pdl_enabled(PDL_CLASS_ATTN_TC) ? 1 : 0;
-  at[1].id = cudaLaunchAttributeClusterDimension;
-  at[1].val.clusterDim.x = (unsigned)nqb; at[1].val.clusterDim.y = 1; at[1].val.clusterDim.z = 1;
-  cfg.attrs = at; cfg.numAttrs = 2;
-  e = cudaLaunchKernelEx(&cfg, k_attn_tc<D, true>, P);
-  if (e != cudaSuccess) return e;
+  { cudaError_t le_ = launch_kc(PDL_CLASS_ATTN_TC, k_attn_tc<D>, dim3(grid), dim3(AT_THREADS), (size_t)(SM::TOTAL), s, P); if (le_ != cudaSuccess) return le_; }
   return cudaGetLastError();
-}
-
-// diagnostics: how many clusters of `nqb` fused-attention CTAs can be resident at once (cudaOccupancyMaxActiveClusters)
-template <int D>
-static int attn_fused_max_clusters_d(int nqb) {
-  using SM = AttnSmem<D>;
-  cudaFuncSetAttribute(k_attn_tc<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL_FUSED);
-  cudaFuncSetAttribute(k_attn_tc<D, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(nqb, 64); cfg.blockDim = dim3(AT_THREADS); cfg.dynamicSmemBytes = SM::TOTAL_FUSED;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = (unsigned)nqb; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-  cfg.attrs = at; cfg.numAttrs = 1;
-  int n = -1;
-  if (cudaOccupancyMaxActiveClusters(&n, k_attn_tc<D, true>, &cfg) != cudaSuccess) { cudaGetLastError(); return -1; }
-  return n;
-}
-int attn_fused_max_clusters(int D, int nqb) {
-  return D == 16 ? attn_fused_max_clusters_d<16>(nqb) : (D == 32 ? attn_fused_max_clusters_d<32>(nqb) : attn_fused_max_clusters_d<64>(nqb));
 }
 
 cudaError_t launch_attn_tc(const AttnTcParams& P, cudaStream_t s) {

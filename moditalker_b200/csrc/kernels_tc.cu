@@ -103,6 +103,37 @@ __global__ void __launch_bounds__(256) k_apply_split(const __grid_constant__ App
   if (P.raw_hi) tc_store_split(rw, P.raw_hi, P.raw_lo, o);
 }
 
+// Channel-sum slots of one GroupNorm group, spread over the lanes that own the group: item i = (channel ci = i % cpg of the
+// group, slot k = i / cpg of the planes involved, in plane order).  All loads of a trip are issued before any is consumed (the
+// slots live in L2: a serial loop over up to 16 slots per channel was a chain of L2 round trips); the assignment of items to
+// lanes is fixed, so the summation order is deterministic.
+struct CsumSrc { const double* cs0; const double* cs1; int C0, C1; };
+__device__ __forceinline__ void csum_group_sum(const CsumSrc& S, const Geo& gs, int b, int p, bool joint, int grp, int cpg,
+                                               int l, int nl /* lanes per group */, double& s, double& ss) {
+  const int n0 = csum_nslots(gs, 0), n1 = csum_nslots(gs, 1);
+  const int nk = joint ? n0 + 2 * n1 : csum_nslots(gs, p);
+  const int nitems = cpg * nk;
+  s = 0.0; ss = 0.0;
+  for (int i0 = l; i0 < nitems; i0 += 4 * nl) {
+    double2 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * nl;
+      v[u] = make_double2(0.0, 0.0);
+      if (i < nitems) {
+        const int k = i / cpg, c = grp * cpg + (i - k * cpg);
+        int pp = p, sl = k;
+        if (joint) { pp = k < n0 ? 0 : (k < n0 + n1 ? 1 : 2); sl = k - (pp == 0 ? 0 : (pp == 1 ? n0 : n0 + n1)); }
+        const double* cs; int Cs, cc;
+        if (c < S.C0) { cs = S.cs0; Cs = S.C0; cc = c; } else { cs = S.cs1; Cs = S.C1; cc = c - S.C0; }
+        v[u] = __ldcg(reinterpret_cast<const double2*>(cs + csum_at(gs, Cs, b, pp, sl, cc)));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { s += v[u].x; ss += v[u].y; }
+  }
+}
+
 // One work unit of the fused GroupNorm-finalise + apply: `chunk_tokens` tokens starting at chunk `chunk_idx` of plane p of
 // sample b, by a 256-thread CTA.  s_aff: 2*C floats, s_mean / s_rstd: 32 doubles each (all CTA-shared scratch).
 __device__ __forceinline__ void apply_norm_unit(const ApplyParams& P, float* s_aff, double* s_mean, double* s_rstd,

@@ -166,11 +166,11 @@ struct MtvHandle_t {
   // feature bits (MTV_TC_MASK): 0-4 op classes on the tensor-core kernel, 5 split-K, 6 tcgen05 attention, 7 small levels,
   // 8 fused GroupNorm statistics, 9 launch fusions, 10 weight L2 prefetch, 11 L2-persisting small-tensor arena;
   // 15 BN = 128 tiles for every split-K-able op, 16 TMA stores of the GEMM epilogue tiles.  (Bits 12 / 13 / 14 were the
-  // persistent chain kernel, the direct A operand and the consumer apply fused into the producer behind a grid barrier: all
-  // measured slower on B200 and removed — profiles/r01_s2_chain_experiment.md, r01_s2_direct_experiment.md,
-  // r02_fused_apply_experiment.md.)
-  // 17 GroupNorm + qkv projection fused into the attention kernel (cluster per (sample, head))
-  int tc_mask = 0x3cfff;
+  // persistent chain kernel, the direct A operand and the consumer apply fused into the producer behind a grid barrier; a
+  // bit 17 fused GroupNorm + qkv into the attention kernel as a cluster front end: all measured slower on B200 and removed —
+  // profiles/r01_s2_chain_experiment.md, r01_s2_direct_experiment.md, r02_fused_apply_experiment.md,
+  // r02_fused_attention_experiment.md.)
+  int tc_mask = 0x1cfff;
   cudaStream_t cap_stream = nullptr;
   cudaStream_t capture_stream() {
     if (!cap_stream) CK(cudaStreamCreateWithFlags(&cap_stream, cudaStreamNonBlocking));
@@ -735,17 +735,9 @@ struct Builder {
       Q.q_hi = dalloc(bytes); Q.q_lo = dalloc(bytes); Q.k_hi = dalloc(bytes); Q.k_lo = dalloc(bytes);
       Q.vt_hi = dalloc(bytes); Q.vt_lo = dalloc(bytes);
     }
-    // ---- fused front end (kernels_attn_tc.cu: attn_front_end): GroupNorm + qkv projection run inside the attention kernel, the
-    // query tiles of one (sample, head) are one cluster — no apply launch, no qkv GEMM launch
-    int nqb = 0;
-    for (int i = 0; i < A.nseg; ++i) nqb += (A.seg_off[i + 1] - A.seg_off[i] + 127) / 128;
-    static const int fe_levels = [] { const char* e = getenv("MTV_FE_LEVELS"); return e ? (int)strtol(e, nullptr, 0) : 0xff; }();   // A/B knob: level bit mask
-    const bool fused_fe = fuse && fuse_gn() && x.csum && ((h->tc_mask >> 17) & 1) && ((fe_levels >> level) & 1) && nqb <= 16 && C <= 1024 && C % 64 == 0;
     // ---- qkv projection
     Tensor qkv;
-    if (fused_fe) {
-      // nothing to launch here
-    } else if (fuse) {             // the GEMM epilogue writes Q / K / V^T directly; no fp32 qkv tensor
+    if (fuse) {             // the GEMM epilogue writes Q / K / V^T directly; no fp32 qkv tensor
       TcOpts o; o.qkv = &Q;
       conv(p + ".qkv", Pq, n, -1, nullptr, 1, false, o);
     } else {
@@ -789,18 +781,6 @@ struct Builder {
       }
       Op op; op.name = "attn_tc:" + p;
       op.flops = 4.0 * B * heads * pairs * D; op.bytes = 4.0 * B * L * 4 * C;
-      if (fused_fe) {
-        T.fe_x = x.p; T.fe_csum = x.csum; T.fe_gamma = h->W(p + ".norm.weight"); T.fe_beta = h->W(p + ".norm.bias");
-        T.fe_bias = h->W(p + ".qkv.bias"); T.fe_joint = a.joint ? 1 : 0; T.fe_geo = geo(level);
-        T.q_hi = Q.q_hi; T.q_lo = Q.q_lo; T.k_hi = Q.k_hi; T.k_lo = Q.k_lo; T.vt_hi = Q.vt_hi; T.vt_lo = Q.vt_lo;
-        const auto& pr = h->tc_w.at(h->W(p + ".qkv.weight"));
-        const uint64_t dims[2] = {(uint64_t)C, (uint64_t)3 * C}; const uint64_t str[1] = {(uint64_t)C * 2};
-        const uint32_t box[2] = {64, (uint32_t)(3 * D)};
-        T.tmWq_hi = make_tmap_bf16(pr.first, 2, dims, str, box);
-        T.tmWq_lo = make_tmap_bf16(pr.second, 2, dims, str, box);
-        op.name = "attn_fused:" + p;
-        op.flops += 2.0 * B * L * 3.0 * C * C; op.bytes += 4.0 * 3.0 * C * C;
-      }
       op.fn = [T](cudaStream_t s) { return launch_attn_tc(T, s); };
       pl->ops.push_back(op);
     } else {
@@ -1166,8 +1146,6 @@ int mtv_debug_read(MtvHandle h, const char* tag, float* dst, int64_t dst_elems, 
     CK(launch_tok2ch(t.p, dst, pl->B, g.L, t.C, (cudaStream_t)stream));
   });
 }
-
-int mtv_debug_max_clusters(int32_t D, int32_t nqb) { return attn_fused_max_clusters(D, nqb); }
 
 int mtv_debug_tc_timing(MtvHandle h, int64_t* records, int32_t cap, int32_t* count) {
   return guarded([&] {

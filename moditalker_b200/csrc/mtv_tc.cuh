@@ -49,37 +49,6 @@ __host__ __device__ inline size_t csum_at(const Geo& g, int C, int b, int p, int
 }
 __host__ __device__ inline size_t csum_elems(const Geo& g, int C, int B) { return (size_t)B * 3 * csum_ns(g) * C * 2; }
 
-// Channel-sum slots of one GroupNorm group, spread over the lanes that own the group: item i = (channel ci = i % cpg of the
-// group, slot k = i / cpg of the planes involved, in plane order).  All loads of a trip are issued before any is consumed (the
-// slots live in L2: a serial loop over up to 16 slots per channel was a chain of L2 round trips); the assignment of items to
-// lanes is fixed, so the summation order is deterministic.
-struct CsumSrc { const double* cs0; const double* cs1; int C0, C1; };
-__device__ __forceinline__ void csum_group_sum(const CsumSrc& S, const Geo& gs, int b, int p, bool joint, int grp, int cpg,
-                                               int l, int nl /* lanes per group */, double& s, double& ss) {
-  const int n0 = csum_nslots(gs, 0), n1 = csum_nslots(gs, 1);
-  const int nk = joint ? n0 + 2 * n1 : csum_nslots(gs, p);
-  const int nitems = cpg * nk;
-  s = 0.0; ss = 0.0;
-  for (int i0 = l; i0 < nitems; i0 += 4 * nl) {
-    double2 v[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int i = i0 + u * nl;
-      v[u] = make_double2(0.0, 0.0);
-      if (i < nitems) {
-        const int k = i / cpg, c = grp * cpg + (i - k * cpg);
-        int pp = p, sl = k;
-        if (joint) { pp = k < n0 ? 0 : (k < n0 + n1 ? 1 : 2); sl = k - (pp == 0 ? 0 : (pp == 1 ? n0 : n0 + n1)); }
-        const double* cs; int Cs, cc;
-        if (c < S.C0) { cs = S.cs0; Cs = S.C0; cc = c; } else { cs = S.cs1; Cs = S.C1; cc = c - S.C0; }
-        v[u] = __ldcg(reinterpret_cast<const double2*>(cs + csum_at(gs, Cs, b, pp, sl, cc)));
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) { s += v[u].x; ss += v[u].y; }
-  }
-}
-
 // D[B*L][Cout] = sum_tap A_tap[B*L][Cin] * W[tap][Cout][Cin]^T   (+bias, +residual)
 struct TcConvParams {
   // L > 128 : taps==9: [0] xy plane (C,W,H,B), [1] yt|xt planes (C,W,H,2,B), 128-token boxes; taps==1: [0] = (C, B*L)
@@ -127,22 +96,9 @@ struct AttnTcParams {
   int B, L, C, heads;
   int nseg; int seg_off[4];
   int dbg_skip;   // diagnostics only (MTV_ATTN_DBG_SKIP; results are garbage): 1 no exp2, 2 no P stores, 4 no row-max exchange, 8 no O fold
-  // Fused front end (fe_x != nullptr; AttentionBlock*.norm + qkv, unet.py:234,251 / 281,297): every CTA first computes
-  // GroupNorm(x) (statistics from the producer's channel-sum slots) and the qkv 1x1 projection of ITS <= 128 tokens for ITS
-  // head on the tensor cores and writes Q / K / V^T (same split-bf16 layouts as the qkv GEMM epilogue); the CTAs of one
-  // (sample, head) are one thread-block cluster and meet at a cluster barrier before the attention proper streams K / V.
-  // No apply launch, no qkv GEMM launch.
-  const float* fe_x;                 // [B][L][C] fp32 block input
-  const double* fe_csum;             // its channel-sum slots (csum_at, geometry fe_geo)
-  const float* fe_gamma; const float* fe_beta;   // norm affine [C]
-  const float* fe_bias;              // qkv bias [3C], head-major q|k|v rows
-  int fe_joint; Geo fe_geo;
-  CUtensorMap tmWq_hi, tmWq_lo;      // qkv weight (C, 3C) split bf16, box (64, 3D)
-  void* q_hi; void* q_lo; void* k_hi; void* k_lo; void* vt_hi; void* vt_lo;
 };
 cudaError_t launch_qkv_split(const QkvSplitParams& P, cudaStream_t s);
 cudaError_t launch_attn_tc(const AttnTcParams& P, cudaStream_t s);
-int         attn_fused_max_clusters(int D, int nqb);   // diagnostics
 
 cudaError_t launch_apply_split(const ApplyParams& P, cudaStream_t s);
 cudaError_t launch_repack_split_w(const float* src, void* hi, void* lo, int Cout, int Cin, int taps, cudaStream_t s);
