@@ -16,6 +16,7 @@
 #include <cstring>
 #include <functional>
 #include <map>
+#include <set>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -379,11 +380,38 @@ struct Builder {
     if (zero) CK(cudaMemset(p, 0, bytes));
     pl->allocs.push_back(p); pl->alloc_bytes += bytes; return p;
   }
+  // ---- workspace reuse.  Activations, operands and split-K scratch are short-lived: a buffer goes back to the pool once the
+  // last op that reads it has been emitted.  Stream order makes that safe (an op writes only after its grid dependency
+  // resolved, i.e. after every earlier op finished, PDL included).  Besides bounding the workspace, reuse keeps the dirty lines
+  // of dead scratch data from being written back to HBM: a buffer that is overwritten ~10 us later is still in L2, whereas
+  // one private buffer per op is evicted by the 529 MB weight stream before its next use (measured: 557 MB of DRAM
+  // writes per B=1 step without reuse, profiles/r02_step_traffic.md).
+  std::multimap<size_t, void*> pool_free; std::unordered_map<void*, size_t> pool_size; std::set<const void*> keep;
+  static size_t pool_round(size_t b) { return (b + 4095) & ~(size_t)4095; }
+  void* palloc(size_t bytes) {
+    const size_t need = pool_round(bytes);
+    auto it = pool_free.lower_bound(need);
+    if (it != pool_free.end() && it->first <= need + need / 4) {     // best fit within 25 %
+      void* p = it->second; pool_free.erase(it); return p;
+    }
+    void* p = dalloc(need);
+    pool_size[p] = need;
+    return p;
+  }
+  void prel(const void* p) {
+    if (!p || keep.count(p)) return;
+    auto it = pool_size.find(const_cast<void*>(p));
+    if (it == pool_size.end()) return;                               // not a pool buffer (persistent allocation)
+    for (auto r = pool_free.equal_range(it->second); r.first != r.second; ++r.first)
+      if (r.first->second == p) return;                              // already released
+    pool_free.emplace(it->second, it->first);
+  }
   Geo geo(int level) const { return level_geo(h->cfg, level); }
   Tensor T(int C, int level) {
     Tensor t; t.C = C; t.level = level;
-    t.p = (float*)dalloc((size_t)B * geo(level).L * C * sizeof(float)); return t;
+    t.p = (float*)palloc((size_t)B * geo(level).L * C * sizeof(float)); return t;
   }
+  void Trel(const Tensor& t) { prel(t.p); }
   void set_segs(int level, bool joint, int& nseg, int* off) const {
     const Geo g = geo(level);
     if (joint) { nseg = 1; off[0] = 0; off[1] = g.L; off[2] = off[3] = g.L; }
@@ -467,11 +495,11 @@ struct Builder {
                       const float* consumer_w = nullptr, int consumer_cout = 0) {
     const int C = S.C0 + S.C1;
     const size_t bytes = (size_t)B * g.L * C * 2;
-    SplitBuf out; out.hi = dalloc(bytes); out.lo = dalloc(bytes);
+    SplitBuf out; out.hi = palloc(bytes); out.lo = palloc(bytes);
     ApplyParams A{};
     A.src0 = S.src0; A.src1 = S.src1; A.C0 = S.C0; A.C1 = S.C1;
     A.silu = S.silu; A.resample = S.resample; A.B = B; A.geo = g; A.hi = out.hi; A.lo = out.lo;
-    if (raw_out) { raw_out->hi = dalloc(bytes); raw_out->lo = dalloc(bytes); A.raw_hi = raw_out->hi; A.raw_lo = raw_out->lo; }
+    if (raw_out) { raw_out->hi = palloc(bytes); raw_out->lo = palloc(bytes); A.raw_hi = raw_out->hi; A.raw_lo = raw_out->lo; }
     if (consumer_w && ((h->tc_mask >> 10) & 1)) {
       auto it = h->tc_w.find(consumer_w);
       if (it != h->tc_w.end()) { A.pf0 = it->second.first; A.pf1 = it->second.second; A.pf_bytes = (unsigned long long)S.taps * C * consumer_cout * 2; }
@@ -567,8 +595,10 @@ struct Builder {
       if (base128 >= 64 || (splittable && ((h->tc_mask >> 15) & 1))) bn = 128;
     }
     T.bn = bn;
+    SplitBuf own0, own1;            // operands this op's own apply launches produce: dead once the GEMM is emitted
     {
       const SplitBuf a0 = o.pre0 ? *o.pre0 : emit_apply(name, S, P.geo, norm0, o.raw_out, S.w, P.Cout);
+      if (!o.pre0) own0 = a0;
       make_A_maps(a0, T.Cin, S.taps, P.geo, T.tmA_hi, T.tmA_lo);
     }
     auto wmaps = [&](const KSeg& K, CUtensorMap& whi, CUtensorMap& wlo) {
@@ -585,6 +615,7 @@ struct Builder {
       const KSeg& X = P.seg[1];
       T.Cin2 = X.C0 + X.C1;
       const SplitBuf a1 = o.pre1 ? *o.pre1 : emit_apply(name + ".skip", X, P.geo, norm1, nullptr);
+      if (!o.pre1) own1 = a1;
       make_A_maps(a1, T.Cin2, 1, P.geo, T.tmA2_hi, T.tmA2_lo);
       wmaps(X, T.tmW2_hi, T.tmW2_lo);
       Ktot += T.Cin2;
@@ -603,7 +634,10 @@ struct Builder {
     T.ksplit = ks;
     const bool coresident = base * ks <= h->num_sms;
     if (ks > 1 && !coresident) throw MtvError("internal: split-K grid is not co-resident at " + name);
-    if (ks > 1) T.partial = (float*)dalloc((size_t)base * ks * 128 * bn * sizeof(float));
+    if (ks > 1) {   // split-K scratch lives only inside its own launch: ONE buffer shared by every split-K op (<= #SMs tiles of 128 x 128 fp32)
+      if (!shared_partial) shared_partial = (float*)dalloc((size_t)h->num_sms * 128 * 128 * sizeof(float));
+      T.partial = shared_partial;
+    }
     if (ks > 1) T.sync = (unsigned long long*)dalloc((size_t)base * 32 * sizeof(unsigned long long), true);   // kernels_tc.cu: TC_SYNC_STRIDE
     Op op; op.name = "conv_tc:" + name; op.launches = 1;
     op.flops = 2.0 * M * P.Cout * Ktot;
@@ -619,7 +653,9 @@ struct Builder {
     op.fn = [tp](cudaStream_t s) { return launch_conv_tc(*tp, s); };
     op.tc = tp;
     pl->ops.push_back(op);
+    prel(own0.hi); prel(own0.lo); prel(own1.hi); prel(own1.lo);
   }
+  float* shared_partial = nullptr;
 
   bool fuse_launches() const { return h->cfg.kernel_path != 1 && ((h->tc_mask >> 9) & 1); }
   void conv(const std::string& name, ConvParams P, int norm0 = -1, int norm1 = -1, Tensor* out_t = nullptr,
@@ -700,6 +736,7 @@ struct Builder {
       TcOpts o; if (have_raw) o.pre1 = &skip_raw;
       conv(p + ".out_layers.3", P, n2, -1, &out, 1, false, o);
     }
+    Trel(hmid); prel(skip_raw.hi); prel(skip_raw.lo);
     return out;
   }
 
@@ -732,8 +769,8 @@ struct Builder {
     if (tc_attn) {
       const size_t bytes = (size_t)B * L * C * 2;
       Q.B = B; Q.L = L; Q.C = C; Q.heads = heads;
-      Q.q_hi = dalloc(bytes); Q.q_lo = dalloc(bytes); Q.k_hi = dalloc(bytes); Q.k_lo = dalloc(bytes);
-      Q.vt_hi = dalloc(bytes); Q.vt_lo = dalloc(bytes);
+      Q.q_hi = palloc(bytes); Q.q_lo = palloc(bytes); Q.k_hi = palloc(bytes); Q.k_lo = palloc(bytes);
+      Q.vt_hi = palloc(bytes); Q.vt_lo = palloc(bytes);
     }
     // ---- qkv projection
     Tensor qkv;
@@ -758,7 +795,7 @@ struct Builder {
       for (int i = 0; i < 4; ++i) T.seg_off[i] = A.seg_off[i];
       if (fuse) {
         const size_t bytes = (size_t)B * L * C * 2;
-        att_split.hi = dalloc(bytes); att_split.lo = dalloc(bytes);
+        att_split.hi = palloc(bytes); att_split.lo = palloc(bytes);
         T.out_hi = att_split.hi; T.out_lo = att_split.lo;
         if ((h->tc_mask >> 10) & 1) {
           auto it = h->tc_w.find(Pp.seg[0].w);
@@ -801,13 +838,21 @@ struct Builder {
       Pp.seg[0].src0 = att.p;
       conv(p + ".proj_out", Pp, -1, -1, &out);
     }
+    // everything between the block input and its output is dead now
+    prel(Q.q_hi); prel(Q.q_lo); prel(Q.k_hi); prel(Q.k_lo); prel(Q.vt_hi); prel(Q.vt_lo);
+    prel(att_split.hi); prel(att_split.lo);
+    if (qkv.p) Trel(qkv);
+    if (att.p) Trel(att);
     return out;
   }
 
   Tensor run_stage(const StageDesc& st, Tensor cur, const Tensor* skip) {
     int level = st.level_in;
     bool first = true;
+    // the stage input and the skip tensor are stage outputs (kept: taps / skip stack); tensors between layers die as soon as
+    // the next layer has been emitted
     for (const Layer& l : st.layers) {
+      const Tensor prev = cur;
       if (l.is_res) {
         const int lo = (l.r.updown == RS_NONE) ? level : (l.r.updown == RS_DOWN2 ? level + 1 : level - 1);
         cur = res_block(l.r, cur, (first && skip) ? skip : nullptr, level, lo);
@@ -815,9 +860,10 @@ struct Builder {
       } else {
         cur = attn_block(l.a, cur, level);
       }
+      if (!first) Trel(prev);
       first = false;
     }
-    if (st.has_joint) cur = attn_block(st.joint, cur, level);
+    if (st.has_joint) { const Tensor prev = cur; cur = attn_block(st.joint, cur, level); if (!first) Trel(prev); }
     return cur;
   }
 
@@ -875,21 +921,21 @@ struct Builder {
       KSeg& S = P.seg[0]; S.src0 = xin.p; S.C0 = xin.C; S.taps = 9; S.w = h->W("input_blocks.0.0.weight");
       P.bias = h->W("input_blocks.0.0.bias"); P.out = cur.p;
       conv("input_blocks.0.0", P, -1, -1, &cur);
-      pl->taps["in0"] = cur; skips.push_back(cur);
+      pl->taps["in0"] = cur; skips.push_back(cur); keep.insert(cur.p);
     }
     for (size_t i = 1; i < A.in.size(); ++i) {
       cur = run_stage(A.in[i], cur, nullptr);
       cur.level = A.in[i].level_out;
-      pl->taps["in" + std::to_string(i)] = cur; skips.push_back(cur);
+      pl->taps["in" + std::to_string(i)] = cur; skips.push_back(cur); keep.insert(cur.p);
     }
     cur = run_stage(A.mid, cur, nullptr);
-    pl->taps["mid"] = cur;
+    pl->taps["mid"] = cur; keep.insert(cur.p);
     for (size_t i = 0; i < A.out.size(); ++i) {
       Tensor sk = skips.back(); skips.pop_back();
       if (sk.C != A.out[i].skip_ch) throw MtvError("internal: skip stack mismatch");
       cur = run_stage(A.out[i], cur, &sk);
       cur.level = A.out[i].level_out;
-      pl->taps["out" + std::to_string(i)] = cur;
+      pl->taps["out" + std::to_string(i)] = cur; keep.insert(cur.p);
     }
     // ---- head: GN -> SiLU -> conv3x3 -> channel-major eps (unet.py:971-975, 1103-1112)
     const int nh = gn("out.0", cur, nullptr, false, h->W("out.0.weight"), h->W("out.0.bias"), -1);

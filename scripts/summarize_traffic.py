@@ -1,6 +1,6 @@
 """Per-kernel-family DRAM traffic and time of one forward from an ncu launch list
 (`ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --csv`).
-usage: python scripts/summarize_traffic.py launches.csv B [out.md] -> merges into profiles/r01_traffic.json"""
+usage: python scripts/summarize_traffic.py launches.csv B [out.md] -> merges into profiles/r02_traffic.json"""
 import csv
 import json
 import os
@@ -8,7 +8,7 @@ import re
 import sys
 from collections import defaultdict
 
-FAMILY = [("k_conv_tc", "conv_tc"), ("k_tc_splitk", "conv_tc"), ("k_attn_tc", "attn_tc"), ("k_apply", "apply"), ("k_conv_simt", "conv"),
+FAMILY = [("k_conv_tc", "conv_tc"), ("k_attn_tc", "attn_tc"), ("k_apply", "apply"), ("k_conv_simt", "conv"),
           ("k_splitk_epilogue", "conv"), ("k_gn_stats", "gn_stats"), ("k_linear_warp", "emb"), ("k_temb", "emb")]
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "nsecond": 1.0, "usecond": 1e3, "msecond": 1e6, "ns": 1.0, "us": 1e3}
 
@@ -50,7 +50,7 @@ print(txt)
 if len(sys.argv) > 3:
     open(sys.argv[3], "w").write(txt)
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-tp = os.path.join(root, "profiles", "r01_traffic.json")
+tp = os.path.join(root, "profiles", "r02_traffic.json")
 data = json.load(open(tp)) if os.path.exists(tp) else {}
 data[f"B{B}"] = {k: {"launches": v["launches"], "dram_bytes": v["dram_bytes"], "ncu_us": v["ns"] / 1e3} for k, v in fam.items()}
 json.dump(data, open(tp, "w"), indent=1, sort_keys=True)
