@@ -138,6 +138,10 @@ __device__ __forceinline__ uint64_t f2_sub(uint64_t a, uint64_t b) { uint64_t r;
 __device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) { uint64_t r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) { uint64_t r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ float max3(float a, float b, float c) { float d; asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c)); return d; }
+__device__ __forceinline__ void a_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ float ex2_approx(float x) {   // 2^x, max rel. error 2^-22; 2^-inf = 0
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -235,7 +239,13 @@ __global__ void __launch_bounds__(AT_THREADS, (D <= 32) ? 2 : 1) k_attn_tc(const
   const uint32_t sP_hi = sStage0 + AT_NS * SM::STAGE, sP_lo = sP_hi + SM::P_SLOT;
 
   // which (segment, query tile), (sample, head)
-  int sg = 0, qb = blockIdx.x;
+  // Split-KV (kv_split > 1, small batches only): the kv_split CTAs of one query tile are one cluster; rank kr streams key blocks
+  // [kr, kr+1) * nblk_seg / kv_split and rank 0 merges the partial (m, l, O) of the others, handed over through distributed
+  // shared memory.  At B=1 a launch has only 32-128 query tiles for 148 SMs and one CTA per SM is latency-bound: twice the CTAs
+  // on the same SMs run the same key blocks in about half the time.
+  const int kvs = P.kv_split > 1 ? P.kv_split : 1;
+  const int kr = kvs > 1 ? (int)(blockIdx.x % kvs) : 0;
+  int sg = 0, qb = kvs > 1 ? (int)(blockIdx.x / kvs) : (int)blockIdx.x;
   for (; sg < P.nseg; ++sg) {
     const int nb = (P.seg_off[sg + 1] - P.seg_off[sg] + AT_BQ - 1) / AT_BQ;
     if (qb < nb) break;
@@ -244,7 +254,9 @@ __global__ void __launch_bounds__(AT_THREADS, (D <= 32) ? 2 : 1) k_attn_tc(const
   const int bh = blockIdx.y;
   const int t_lo = P.seg_off[sg], len = P.seg_off[sg + 1] - t_lo;
   const int q0 = qb * AT_BQ;
-  const int nblk = (len + AT_BKV - 1) / AT_BKV;
+  const int nblk_seg = (len + AT_BKV - 1) / AT_BKV;
+  const int jb0 = (kr * nblk_seg) / kvs;                       // first key block of this rank
+  const int nblk = ((kr + 1) * nblk_seg) / kvs - jb0;          // host guarantees >= 1
 
   if (threadIdx.x == 0) {
     a_mbar_init(&bar_q, 1);
@@ -284,11 +296,11 @@ __global__ void __launch_bounds__(AT_THREADS, (D <= 32) ? 2 : 1) k_attn_tc(const
           const uint32_t sK_hi = sStage0 + stage * SM::STAGE, sK_lo = sK_hi + SM::K_SLOT;
           const uint32_t sV_hi = sK_lo + SM::K_SLOT, sV_lo = sV_hi + SM::V_SLOT;
           const uint32_t fb = a_smem_u32(&bar_full[stage]);
-          const int krow = bh * P.L + t_lo + j * AT_BKV;
+          const int krow = bh * P.L + t_lo + (jb0 + j) * AT_BKV;
           a_tma_2d(sK_hi, &P.tmK_hi, fb, 0, krow);
           a_tma_2d(sK_lo, &P.tmK_lo, fb, 0, krow);
-          a_tma_2d(sV_hi, &P.tmV_hi, fb, t_lo + j * AT_BKV, bh * D);
-          a_tma_2d(sV_lo, &P.tmV_lo, fb, t_lo + j * AT_BKV, bh * D);
+          a_tma_2d(sV_hi, &P.tmV_hi, fb, t_lo + (jb0 + j) * AT_BKV, bh * D);
+          a_tma_2d(sV_lo, &P.tmV_lo, fb, t_lo + (jb0 + j) * AT_BKV, bh * D);
         }
         __syncwarp();
         if (++stage == AT_NS) { stage = 0; phase ^= 1u; }
@@ -296,6 +308,7 @@ __global__ void __launch_bounds__(AT_THREADS, (D <= 32) ? 2 : 1) k_attn_tc(const
     }
     a_mbar_wait(&bar_o_full, (uint32_t)((nblk - 1) & 1));   // all threads trigger when only the epilogue remains
     MTV_PDL_TRIGGER();
+    if (kvs > 1) a_cluster_sync();
   } else if (warp == 1) {
     // =============================== MMA issuer =================================
     // whole warp in the loop, one elected lane issues; descriptors = base descriptor + (byte offset >> 4)
@@ -357,6 +370,7 @@ __global__ void __launch_bounds__(AT_THREADS, (D <= 32) ? 2 : 1) k_attn_tc(const
     }
     a_mbar_wait(&bar_o_full, (uint32_t)((nblk - 1) & 1));
     MTV_PDL_TRIGGER();
+    if (kvs > 1) a_cluster_sync();
   } else {
     // =============================== softmax / epilogue ==========================
     // warps 2-5: key columns [0,32) of each S block and output columns [0, D/2);
@@ -397,7 +411,7 @@ __global__ void __launch_bounds__(AT_THREADS, (D <= 32) ? 2 : 1) k_attn_tc(const
       a_fence_before();
       __syncwarp();
       if (lane == 0) a_mbar_arrive(&bar_s_free);            // S TMEM may be overwritten by S(j+1)
-      const int valid = len - j * AT_BKV - half * 32;       // >= 32 except in the last block (may be <= 0 there)
+      const int valid = len - (jb0 + j) * AT_BKV - half * 32;       // >= 32 except in the segment's last block (may be <= 0 there)
       if (valid < 32) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) if (i >= valid) s[i] = -INFINITY;
@@ -489,9 +503,39 @@ __global__ void __launch_bounds__(AT_THREADS, (D <= 32) ? 2 : 1) k_attn_tc(const
     asm volatile("bar.sync 1, 256;" ::: "memory");          // all max-exchange reads done before the slots are reused
     s_xchg[0][half][row] = l_part;
     asm volatile("bar.sync 1, 256;" ::: "memory");
-    const float l_run = l_part + s_xchg[0][half ^ 1][row];
+    float l_run = l_part + s_xchg[0][half ^ 1][row];
+    if (kvs > 1) {
+      // partial results of ranks > 0 -> rank 0's merge buffer [rank - 1][row][D + 2] = O[D] | m | l (distributed shared memory)
+      float* mbuf = reinterpret_cast<float*>(smem_raw + (smem0 - a_smem_u32(smem_raw)) + SM::TOTAL - 1024);
+      constexpr int MW = D + 2;
+      if (kr > 0) {
+        const uint32_t local = a_smem_u32(mbuf + ((size_t)(kr - 1) * AT_BQ + row) * MW + half * DH);
+        uint32_t remote;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(0));
+#pragma unroll
+        for (int d = 0; d < DH; ++d) asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(remote + 4u * d), "f"(o[d]) : "memory");
+        if (half == 0) {
+          const uint32_t ml = remote + 4u * D;
+          asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(ml), "f"(m_run) : "memory");
+          asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(ml + 4u), "f"(l_run) : "memory");
+        }
+      }
+      a_cluster_sync();
+      if (kr == 0) {
+        for (int r = 1; r < kvs; ++r) {        // fixed order: deterministic
+          const float* src = mbuf + ((size_t)(r - 1) * AT_BQ + row) * MW;
+          const float m_r = src[D], l_r = src[D + 1];
+          const float m_new = fmaxf(m_run, m_r);
+          const float s0 = ex2_approx(m_run - m_new), s1 = ex2_approx(m_r - m_new);
+#pragma unroll
+          for (int d = 0; d < DH; ++d) o[d] = o[d] * s0 + src[half * DH + d] * s1;
+          l_run = l_run * s0 + l_r * s1;
+          m_run = m_new;
+        }
+      }
+    }
     const int q = q0 + row;
-    if (q < len) {
+    if (q < len && kr == 0) {
       const int b = bh / P.heads, h = bh - b * P.heads;
       const float inv = 1.0f / l_run;
       const size_t oidx = ((size_t)b * P.L + t_lo + q) * P.C + h * D + half * DH;
@@ -528,12 +572,32 @@ __global__ void __launch_bounds__(AT_THREADS, (D <= 32) ? 2 : 1) k_attn_tc(const
 template <int D>
 static cudaError_t launch_attn_tc_d(const AttnTcParams& P, cudaStream_t s) {
   using SM = AttnSmem<D>;
-  cudaError_t e = cudaFuncSetAttribute(k_attn_tc<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL);
-  if (e != cudaSuccess) return e;
+  const int kvs = P.kv_split > 1 ? P.kv_split : 1;
+  if (kvs > 8) return cudaErrorInvalidValue;
   int nqb = 0;
-  for (int i = 0; i < P.nseg; ++i) nqb += (P.seg_off[i + 1] - P.seg_off[i] + AT_BQ - 1) / AT_BQ;
-  dim3 grid(nqb, P.B * P.heads);
-  { cudaError_t le_ = launch_kc(PDL_CLASS_ATTN_TC, k_attn_tc<D>, dim3(grid), dim3(AT_THREADS), (size_t)(SM::TOTAL), s, P); if (le_ != cudaSuccess) return le_; }
+  for (int i = 0; i < P.nseg; ++i) {
+    const int len = P.seg_off[i + 1] - P.seg_off[i];
+    nqb += (len + AT_BQ - 1) / AT_BQ;
+    if ((len + AT_BKV - 1) / AT_BKV < kvs) return cudaErrorInvalidValue;      // every rank needs at least one key block
+  }
+  const size_t smem = (size_t)SM::TOTAL + (kvs > 1 ? (size_t)(kvs - 1) * AT_BQ * (D + 2) * sizeof(float) : 0);
+  if (smem > 227u * 1024u) return cudaErrorInvalidValue;
+  // the attribute is a per-function maximum: keep it at the largest size any launch of this head dim has asked for
+  static size_t smem_max = 0;
+  cudaError_t e = cudaSuccess;
+  if (smem > smem_max) { e = cudaFuncSetAttribute(k_attn_tc<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); smem_max = smem; }
+  if (e != cudaSuccess) return e;
+  dim3 grid(nqb * kvs, P.B * P.heads);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = dim3(AT_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = mtv_pdl_enabled(PDL_CLASS_ATTN_TC) ? 1 : 0;
+  at[1].id = cudaLaunchAttributeClusterDimension;
+  at[1].val.clusterDim.x = (unsigned)kvs; at[1].val.clusterDim.y = 1; at[1].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = kvs > 1 ? 2 : 1;
+  e = cudaLaunchKernelEx(&cfg, k_attn_tc<D>, P);
+  if (e != cudaSuccess) return e;
   return cudaGetLastError();
 }
 

@@ -816,6 +816,19 @@ struct Builder {
         const uint32_t bv[2] = {64, (uint32_t)D};
         T.tmV_hi = make_tmap_bf16(Q.vt_hi, 2, dims, str, bv, 128); T.tmV_lo = make_tmap_bf16(Q.vt_lo, 2, dims, str, bv, 128);
       }
+      {
+        // split-KV: when the launch has fewer CTAs than SMs (one latency-bound CTA per SM), 2 CTAs share each query tile
+        int nqb = 0, min_blk = 1 << 30;
+        for (int i = 0; i < A.nseg; ++i) {
+          const int len = A.seg_off[i + 1] - A.seg_off[i];
+          nqb += (len + 127) / 128; min_blk = std::min(min_blk, (len + 63) / 64);
+        }
+        static const int kvs_max = [] { const char* e = getenv("MTV_ATTN_KV_SPLIT"); return e ? std::max(1, atoi(e)) : 2; }();   // 4 measured no better than 2 (profiles/r02_attention.md)
+        int kvs = 1;
+        const int cap = D == 64 ? 2 : 4;       // rank 0's merge buffer (kvs - 1) x 128 x (D + 2) floats must fit next to the K / V ring
+        while (kvs * 2 <= std::min(kvs_max, cap) && nqb * B * heads * kvs < h->num_sms && min_blk >= 2 * kvs * 2) kvs *= 2;   // >= 2 key blocks per rank
+        T.kv_split = kvs;
+      }
       Op op; op.name = "attn_tc:" + p;
       op.flops = 4.0 * B * heads * pairs * D; op.bytes = 4.0 * B * L * 4 * C;
       op.fn = [T](cudaStream_t s) { return launch_attn_tc(T, s); };

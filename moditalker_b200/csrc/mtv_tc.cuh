@@ -96,6 +96,7 @@ struct AttnTcParams {
   int B, L, C, heads;
   int nseg; int seg_off[4];
   int dbg_skip;   // diagnostics only (MTV_ATTN_DBG_SKIP; results are garbage): 1 no exp2, 2 no P stores, 4 no row-max exchange, 8 no O fold
+  int kv_split;   // > 1: that many CTAs (one cluster) share a query tile, each streaming 1/kv_split of the key blocks (small batches)
 };
 cudaError_t launch_qkv_split(const QkvSplitParams& P, cudaStream_t s);
 cudaError_t launch_attn_tc(const AttnTcParams& P, cudaStream_t s);
