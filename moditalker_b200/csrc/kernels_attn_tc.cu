@@ -20,6 +20,7 @@
 #include "mtv_tc.cuh"
 
 #include <cuda_bf16.h>
+#include <cstdio>
 
 namespace mtv {
 
@@ -101,6 +102,10 @@ __device__ __forceinline__ void a_tmem_st16(uint32_t taddr, const uint32_t (&r)[
       "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
       ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
         "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+__device__ __forceinline__ void a_tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
 }
 __device__ __forceinline__ void a_tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void a_commit(uint64_t* bar) {
@@ -198,12 +203,8 @@ cudaError_t launch_qkv_split(const QkvSplitParams& P, cudaStream_t s) {
 // ------------------------------------------------------------------ attention
 constexpr int AT_BQ = 128, AT_BKV = 64, AT_THREADS = 320, AT_NS = 3;   // warps: 0 TMA, 1 MMA, 2-5 / 6-9 softmax halves
 // P (softmax probabilities, split bf16) is handed to the PV MMA through TENSOR MEMORY (tcgen05.st by the softmax threads, A operand
-// of tcgen05.mma read from TMEM): the kernel was shared-memory-bandwidth bound at head dim 16 — per 64-key block 32 KB of P stores
-// and 48 KB of MMA re-reads of P against 8 KB of K / V — and "no P stores" alone was worth -21 % (profiles/r01_s2_attention_skip.md)
-#ifndef MTV_ATTN_P_IN_TMEM
-#define MTV_ATTN_P_IN_TMEM 1
-#endif
-constexpr bool AT_P_IN_TMEM = MTV_ATTN_P_IN_TMEM != 0;
+// of tcgen05.mma read from TMEM): through shared memory the kernel was smem-bandwidth bound at head dim 16 — per 64-key block 32 KB
+// of P stores and 48 KB of MMA re-reads of P against 8 KB of K / V (profiles/r01_s2_attention_skip.md)
 
 template <int D>
 struct AttnSmem {
@@ -214,8 +215,7 @@ struct AttnSmem {
   static constexpr int align_up(int v) { return (v + 1023) & ~1023; }
   static constexpr int Q_SLOT = align_up(Q_BYTES), K_SLOT = align_up(K_BYTES), V_SLOT = align_up(V_BYTES);
   static constexpr int STAGE = 2 * K_SLOT + 2 * V_SLOT;
-  static constexpr int P_SLOT = AT_BQ * 128;               // P tile: 128 rows x 64 keys bf16 (only when P goes through smem)
-  static constexpr int TOTAL = 2 * Q_SLOT + AT_NS * STAGE + (AT_P_IN_TMEM ? 0 : 2 * P_SLOT) + 1024;
+  static constexpr int TOTAL = 2 * Q_SLOT + AT_NS * STAGE + 1024;
   static constexpr int STAGE_TX = 2 * K_BYTES + 2 * V_BYTES;
 };
 
@@ -225,10 +225,15 @@ __global__ void __launch_bounds__(AT_THREADS, (D <= 32) ? 2 : 1) k_attn_tc(const
   mtv_prefetch_slice(P.pf0, P.pf1, P.pf_bytes, blockIdx.x + gridDim.x * blockIdx.y, gridDim.x * gridDim.y);
   constexpr uint32_t IDESC_S = a_idesc(AT_BQ, AT_BKV);
   constexpr uint32_t IDESC_O = a_idesc(AT_BQ, D);
-  // S: cols [0,64), O block: cols [64, 64+D), P_hi: [128,160), P_lo: [160,192) (bf16 pairs, 64 keys)
-  constexpr int TMEM_COLS = AT_P_IN_TMEM ? 256 : 128;
+  // D <= 32: V_hi and V_lo tiles are adjacent in smem, so ONE MMA with N = 2D computes [P_hi V_hi | P_hi V_lo] into O columns
+  // [0,D) | [D,2D) and a second adds P_lo V_hi into [0,D): 8 instead of 12 tcgen05.mma per key block (the kernel is bound by the
+  // NUMBER of small MMAs: ~58 tensor-pipe cycles each whatever N); the two column groups are summed once at the end
+  constexpr bool STACK_V = D <= 32;
+  constexpr uint32_t IDESC_O2 = a_idesc(AT_BQ, 2 * D);
+  static_assert(!STACK_V || AttnSmem<D>::V_SLOT == AttnSmem<D>::V_BYTES, "stacked V needs contiguous hi / lo tiles");
+  constexpr int TMEM_COLS = 256;
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bar_q, bar_full[AT_NS], bar_empty[AT_NS], bar_s_full, bar_s_free, bar_p_full, bar_o_full;
+  __shared__ __align__(8) uint64_t bar_q, bar_full[AT_NS], bar_empty[AT_NS], bar_s_full, bar_s_free, bar_p_full[2], bar_pv_done[2];
   __shared__ uint32_t tmem_base_s;
   __shared__ float s_xchg[2][2][AT_BQ];   // [block parity][half][row]: row max (and the final row sum) exchange
 
@@ -236,7 +241,6 @@ __global__ void __launch_bounds__(AT_THREADS, (D <= 32) ? 2 : 1) k_attn_tc(const
   const uint32_t smem0 = (a_smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sQ_hi = smem0, sQ_lo = smem0 + SM::Q_SLOT;
   const uint32_t sStage0 = smem0 + 2 * SM::Q_SLOT;
-  const uint32_t sP_hi = sStage0 + AT_NS * SM::STAGE, sP_lo = sP_hi + SM::P_SLOT;
 
   // which (segment, query tile), (sample, head)
   // Split-KV (kv_split > 1, small batches only): the kv_split CTAs of one query tile are one cluster; rank kr streams key blocks
@@ -261,9 +265,9 @@ __global__ void __launch_bounds__(AT_THREADS, (D <= 32) ? 2 : 1) k_attn_tc(const
   if (threadIdx.x == 0) {
     a_mbar_init(&bar_q, 1);
     for (int s = 0; s < AT_NS; ++s) { a_mbar_init(&bar_full[s], 1); a_mbar_init(&bar_empty[s], 1); }
-    a_mbar_init(&bar_s_full, 1); a_mbar_init(&bar_o_full, 1);
+    a_mbar_init(&bar_s_full, 1); a_mbar_init(&bar_pv_done[0], 1); a_mbar_init(&bar_pv_done[1], 1);
     // one arrival per softmax WARP (8), not per thread: 256 same-address mbarrier arrivals per key block serialise in shared memory
-    a_mbar_init(&bar_s_free, 8); a_mbar_init(&bar_p_full, 8);
+    a_mbar_init(&bar_s_free, 8); a_mbar_init(&bar_p_full[0], 8); a_mbar_init(&bar_p_full[1], 8);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -275,8 +279,11 @@ __global__ void __launch_bounds__(AT_THREADS, (D <= 32) ? 2 : 1) k_attn_tc(const
   __syncthreads();
   a_fence_after();
   const uint32_t tmem_base = tmem_base_s;
+  // S: cols [0,64), O (accumulated over ALL key blocks): [64, 64+D), P double-buffered: buffer b at 128 + 64 b = P_hi (32 cols of
+  // packed bf16 pairs) | P_lo (32)
   const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 64;
-  const uint32_t tmem_Phi = tmem_base + 128, tmem_Plo = tmem_base + 160;
+  const uint32_t tmem_P = tmem_base + 128;
+  const uint32_t last_pv_par = (uint32_t)(((nblk - 1) >> 1) & 1);      // phase parity of the last PV commit on bar_pv_done[(nblk-1)&1]
   MTV_PDL_WAIT();        // Q / K / V^T are written by the preceding k_qkv_split
 
   if (warp == 0) {
@@ -306,7 +313,7 @@ __global__ void __launch_bounds__(AT_THREADS, (D <= 32) ? 2 : 1) k_attn_tc(const
         if (++stage == AT_NS) { stage = 0; phase ^= 1u; }
       }
     }
-    a_mbar_wait(&bar_o_full, (uint32_t)((nblk - 1) & 1));   // all threads trigger when only the epilogue remains
+    a_mbar_wait(&bar_pv_done[(nblk - 1) & 1], last_pv_par);   // all threads trigger when only the epilogue remains
     MTV_PDL_TRIGGER();
     if (kvs > 1) a_cluster_sync();
   } else if (warp == 1) {
@@ -344,31 +351,32 @@ __global__ void __launch_bounds__(AT_THREADS, (D <= 32) ? 2 : 1) k_attn_tc(const
           a_fence_after();
           issue_S(nstage);
         }
-        a_mbar_wait(&bar_p_full, (uint32_t)(j & 1));        // P(j) is in smem, O block (j-1) was consumed
+        a_mbar_wait(&bar_p_full[j & 1], (uint32_t)((j >> 1) & 1));   // P(j) is in tensor memory (and every correction of O is done)
         a_fence_after();
         const uint32_t sV_hi = sStage0 + stage * SM::STAGE + 2 * SM::K_SLOT, sV_lo = sV_hi + SM::V_SLOT;
-        const uint64_t ph0 = dPV + off16(sP_hi), pl0 = dPV + off16(sP_lo), vh0 = dPV + off16(sV_hi), vl0 = dPV + off16(sV_lo);
+        const uint64_t vh0 = dPV + off16(sV_hi), vl0 = dPV + off16(sV_lo);
+        (void)vl0;
+        const uint32_t tP_hi = tmem_P + (uint32_t)((j & 1) * 64), tP_lo = tP_hi + 32;
         if (a_elect_one()) {
 #pragma unroll
-          for (int k = 0; k < AT_BKV / 16; ++k) {
-            if constexpr (AT_P_IN_TMEM) {
-              a_mma_ts(tmem_O, tmem_Phi + 8 * k, vh0 + 2 * k, IDESC_O, k > 0 ? 1u : 0u);
-              a_mma_ts(tmem_O, tmem_Plo + 8 * k, vh0 + 2 * k, IDESC_O, 1u);
-              a_mma_ts(tmem_O, tmem_Phi + 8 * k, vl0 + 2 * k, IDESC_O, 1u);
+          for (int k = 0; k < AT_BKV / 16; ++k) {       // O += P(j) V(j): the accumulator lives in tensor memory across key blocks
+            if constexpr (STACK_V) {
+              a_mma_ts(tmem_O, tP_hi + 8 * k, vh0 + 2 * k, IDESC_O2, (j | k) ? 1u : 0u);
+              a_mma_ts(tmem_O, tP_lo + 8 * k, vh0 + 2 * k, IDESC_O, 1u);
             } else {
-              a_mma(tmem_O, ph0 + 2 * k, vh0 + 2 * k, IDESC_O, k > 0 ? 1u : 0u);
-              a_mma(tmem_O, pl0 + 2 * k, vh0 + 2 * k, IDESC_O, 1u);
-              a_mma(tmem_O, ph0 + 2 * k, vl0 + 2 * k, IDESC_O, 1u);
+              a_mma_ts(tmem_O, tP_hi + 8 * k, vh0 + 2 * k, IDESC_O, (j | k) ? 1u : 0u);
+              a_mma_ts(tmem_O, tP_lo + 8 * k, vh0 + 2 * k, IDESC_O, 1u);
+              a_mma_ts(tmem_O, tP_hi + 8 * k, vl0 + 2 * k, IDESC_O, 1u);
             }
           }
-          a_commit(&bar_o_full);
+          a_commit(&bar_pv_done[j & 1]);
           a_commit(&bar_empty[stage]);
         }
         __syncwarp();
         stage = nstage; phase = nphase;
       }
     }
-    a_mbar_wait(&bar_o_full, (uint32_t)((nblk - 1) & 1));
+    a_mbar_wait(&bar_pv_done[(nblk - 1) & 1], last_pv_par);
     MTV_PDL_TRIGGER();
     if (kvs > 1) a_cluster_sync();
   } else {
@@ -380,26 +388,22 @@ __global__ void __launch_bounds__(AT_THREADS, (D <= 32) ? 2 : 1) k_attn_tc(const
     const int qq = warp & 3;                      // TMEM lane quarter this warp may read
     const int row = qq * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(qq * 32) << 16;
+    // Lazy rescaling: O accumulates in tensor memory under a reference maximum m_run that is only raised when the row maximum
+    // has grown by more than 2^8 (then O and l are rescaled once, exactly); otherwise p = 2^(s - m_run) <= 256 is used as is.
+    // The softmax warps therefore never wait for a PV product in the steady state: the chain per key block is
+    // S -> tcgen05.ld -> max -> ex2 -> P (tcgen05.st into the buffer the MMA warp is not reading) -> arrive.
     float m_run = -INFINITY, l_part = 0.f;
     float o[DH];
-#pragma unroll
-    for (int d = 0; d < DH; ++d) o[d] = 0.f;
-
-    auto fold_O = [&]() {   // o += this half's columns of O_blk (TMEM cols [64 + half*DH, +DH))
-#pragma unroll
-      for (int c = 0; c < DH; c += 8) {
-        uint32_t r[8];
-        a_tmem_ld8(tmem_O + lane_addr + (uint32_t)(half * DH + c), r);
-        a_tmem_wait_ld();
-#pragma unroll
-        for (int i = 0; i < 8; i += 2)
-          f2_unpack(f2_add(f2_pack(o[c + i], o[c + i + 1]), f2_pack(__uint_as_float(r[i]), __uint_as_float(r[i + 1]))), o[c + i], o[c + i + 1]);
-      }
-    };
+    // diagnostics (MTV_ATTN_DBG_SKIP bit 5): cycles per phase of the softmax loop, summed over the key blocks, thread 64 of CTA (0, 0)
+    const bool prof = (P.dbg_skip & 32) && threadIdx.x == 64 && blockIdx.x == 0 && blockIdx.y == 0;
+    long long tph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tq = 0;
+#define AT_STAMP(i) do { if (prof) { const long long t_ = clock64(); tph[i] += t_ - tq; tq = t_; } } while (0)
+    if (prof) tq = clock64();
 
     for (int j = 0; j < nblk; ++j) {
       a_mbar_wait(&bar_s_full, (uint32_t)(j & 1));
       a_fence_after();
+      AT_STAMP(0);
       float s[32];
       {
         uint32_t r[32];
@@ -411,6 +415,7 @@ __global__ void __launch_bounds__(AT_THREADS, (D <= 32) ? 2 : 1) k_attn_tc(const
       a_fence_before();
       __syncwarp();
       if (lane == 0) a_mbar_arrive(&bar_s_free);            // S TMEM may be overwritten by S(j+1)
+      AT_STAMP(1);
       const int valid = len - (jb0 + j) * AT_BKV - half * 32;       // >= 32 except in the segment's last block (may be <= 0 there)
       if (valid < 32) {
 #pragma unroll
@@ -425,11 +430,35 @@ __global__ void __launch_bounds__(AT_THREADS, (D <= 32) ? 2 : 1) k_attn_tc(const
       asm volatile("bar.sync 1, 256;" ::: "memory");
       mx = fmaxf(mx, s_xchg[j & 1][half ^ 1][row]);
       }
-      const float m_new = fmaxf(m_run, mx);                 // finite: the lower half always holds a valid key
-      const float corr = ex2_approx(m_run - m_new);
+      AT_STAMP(2);
+      // both threads of a row see the same mx and take the same decision (finite: the lower half always holds a valid key)
+      if (j == 0) {
+        m_run = mx;
+      } else if (mx > m_run + 8.0f) {
+        // rare after the first blocks: rescale this row of O (our DH columns) and l.  PV(j-1) must have finished accumulating.
+        a_mbar_wait(&bar_pv_done[(j - 1) & 1], (uint32_t)(((j - 1) >> 1) & 1));
+        a_fence_after();
+        const float corr = ex2_approx(m_run - mx);
+#pragma unroll
+        for (int g = 0; g < (STACK_V ? 2 : 1); ++g) {
+#pragma unroll
+          for (int c = 0; c < DH; c += 8) {
+            uint32_t r[8];
+            a_tmem_ld8(tmem_O + lane_addr + (uint32_t)(g * D + half * DH + c), r);
+            a_tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * corr);
+            a_tmem_st8(tmem_O + lane_addr + (uint32_t)(g * D + half * DH + c), r);
+          }
+        }
+        a_tmem_wait_st();
+        l_part *= corr;
+        m_run = mx;
+      }
+      AT_STAMP(3);
       float sum0 = 0.f, sum1 = 0.f;
       if (!(P.dbg_skip & 1)) {
-        const uint64_t mm = f2_pack(m_new, m_new);
+        const uint64_t mm = f2_pack(m_run, m_run);
         uint64_t sums = f2_pack(0.f, 0.f);
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
@@ -440,65 +469,59 @@ __global__ void __launch_bounds__(AT_THREADS, (D <= 32) ? 2 : 1) k_attn_tc(const
         f2_unpack(sums, sum0, sum1);
       } else {
 #pragma unroll
-      for (int i = 0; i < 32; i += 2) { s[i] = s[i] - m_new; s[i + 1] = s[i + 1] - m_new; sum0 += s[i]; sum1 += s[i + 1]; }
+      for (int i = 0; i < 32; i += 2) { s[i] = s[i] - m_run; s[i + 1] = s[i + 1] - m_run; sum0 += s[i]; sum1 += s[i + 1]; }
       }
-      if (j > 0) {                                          // O block (j-1) finished -> fold it in before rescaling
-        a_mbar_wait(&bar_o_full, (uint32_t)((j - 1) & 1));
-        a_fence_after();
-        if (!(P.dbg_skip & 8)) fold_O();
+      l_part += sum0 + sum1;
+      // this thread's 32 keys of its row -> 16 packed columns each of P_hi / P_lo (key 2e in the low half of column e):
+      // hi = bf16x2(p), lo = bf16x2(p - float(hi))
+      uint32_t hi[16], lo[16];
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        const float p0 = s[2 * e], p1 = s[2 * e + 1];
+        hi[e] = cvt_bf16x2(p0, p1);
+        float l0, l1;
+        f2_unpack(f2_sub(f2_pack(p0, p1), f2_pack(__uint_as_float(hi[e] << 16), __uint_as_float(hi[e] & 0xffff0000u))), l0, l1);
+        lo[e] = cvt_bf16x2(l0, l1);
       }
-      l_part = l_part * corr + (sum0 + sum1);
-      m_run = m_new;
-      {
-        const uint64_t cc = f2_pack(corr, corr);
-#pragma unroll
-        for (int d = 0; d < DH; d += 2) f2_unpack(f2_mul(f2_pack(o[d], o[d + 1]), cc), o[d], o[d + 1]);
+      AT_STAMP(4);
+      // P buffer (j & 1) was last read by PV(j-2)
+      if (j >= 2) { a_mbar_wait(&bar_pv_done[j & 1], (uint32_t)(((j >> 1) - 1) & 1)); a_fence_after(); }
+      AT_STAMP(5);
+      if (!(P.dbg_skip & 2)) {
+        const uint32_t tP = tmem_P + (uint32_t)((j & 1) * 64) + lane_addr + (uint32_t)(half * 16);
+        a_tmem_st16(tP, hi);
+        a_tmem_st16(tP + 32, lo);
+        a_tmem_wait_st();
       }
-      // P(j) -> smem, split bf16, 128B-swizzled K-major rows (16-byte chunk c of row r at c ^ (r & 7));
-      // this half owns chunks [4*half, 4*half + 4).  hi = bf16x2(p), lo = bf16x2(p - float(hi)): 3 instr / element
-      if constexpr (AT_P_IN_TMEM) {
-        // this thread's 32 keys of its row -> 16 packed columns each of P_hi / P_lo (key 2e in the low half of column e)
-        uint32_t hi[16], lo[16];
-#pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          const float p0 = s[2 * e], p1 = s[2 * e + 1];
-          hi[e] = cvt_bf16x2(p0, p1);
-          float l0, l1;
-          f2_unpack(f2_sub(f2_pack(p0, p1), f2_pack(__uint_as_float(hi[e] << 16), __uint_as_float(hi[e] & 0xffff0000u))), l0, l1);
-          lo[e] = cvt_bf16x2(l0, l1);
-        }
-        if (!(P.dbg_skip & 2)) {
-          a_tmem_st16(tmem_Phi + lane_addr + (uint32_t)(half * 16), hi);
-          a_tmem_st16(tmem_Plo + lane_addr + (uint32_t)(half * 16), lo);
-          a_tmem_wait_st();
-        }
-      } else if (!(P.dbg_skip & 2)) {   // P through shared memory
-        const uint32_t rbase_hi = sP_hi + (uint32_t)row * 128u, rbase_lo = sP_lo + (uint32_t)row * 128u;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint32_t hi[4], lo[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float p0 = s[c * 8 + 2 * e], p1 = s[c * 8 + 2 * e + 1];
-            hi[e] = cvt_bf16x2(p0, p1);
-            lo[e] = cvt_bf16x2(p0 - __uint_as_float(hi[e] << 16), p1 - __uint_as_float(hi[e] & 0xffff0000u));
-          }
-          const uint32_t off = (uint32_t)((((half << 2) | c) ^ (row & 7)) * 16);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rbase_hi + off), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rbase_lo + off), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
-        }
-      }
-      if (!AT_P_IN_TMEM) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA (async proxy)
       a_fence_before();
       __syncwarp();
-      if (lane == 0) a_mbar_arrive(&bar_p_full);
+      if (lane == 0) a_mbar_arrive(&bar_p_full[j & 1]);
+      AT_STAMP(6);
       // s_xchg is double-buffered by block parity: slot (j & 1) is rewritten in block j + 2, i.e. after the
       // bar.sync of block j + 1, which every reader of block j has passed by then
     }
-    a_mbar_wait(&bar_o_full, (uint32_t)((nblk - 1) & 1));
+    a_mbar_wait(&bar_pv_done[(nblk - 1) & 1], last_pv_par);
+    AT_STAMP(7);
+    if (prof)
+      printf("attn D=%d L=%d nblk=%d cycles/block: wait_S %lld ld_S %lld max+xchg %lld corr %lld exp+cvt %lld wait_Pbuf %lld st_P+arrive %lld | tail %lld\n", D, P.L, nblk,
+             tph[0] / nblk, tph[1] / nblk, tph[2] / nblk, tph[3] / nblk, tph[4] / nblk, tph[5] / nblk, tph[6] / nblk, tph[7]);
+#undef AT_STAMP
     MTV_PDL_TRIGGER();
     a_fence_after();
-    fold_O();
+#pragma unroll
+    for (int c = 0; c < DH; c += 8) {     // the finished accumulator: this half's columns of O
+      uint32_t r[8];
+      a_tmem_ld8(tmem_O + lane_addr + (uint32_t)(half * DH + c), r);
+      a_tmem_wait_ld();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[c + i] = __uint_as_float(r[i]);
+      if constexpr (STACK_V) {
+        a_tmem_ld8(tmem_O + lane_addr + (uint32_t)(D + half * DH + c), r);
+        a_tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[c + i] += __uint_as_float(r[i]);
+      }
+    }
     // total row sum = both halves' partial sums
     asm volatile("bar.sync 1, 256;" ::: "memory");          // all max-exchange reads done before the slots are reused
     s_xchg[0][half][row] = l_part;
