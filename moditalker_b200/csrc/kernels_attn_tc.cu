@@ -36,8 +36,22 @@ __device__ __forceinline__ void a_mbar_expect_tx(uint64_t* bar, uint32_t bytes) 
 __device__ __forceinline__ void a_mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a_smem_u32(bar)) : "memory");
 }
-// Bounded: a pipeline bug must surface as a launch failure (trap), never as a hung GPU.
+// The softmax warps wait with the bare retry loop: ANY extra instruction in it (a failure counter, a back-off) measured 6-7 % of
+// the whole kernel on B200 (ten inlined wait sites per key block; profiles/r02_attention.md).  The hang guard lives in the two
+// single-purpose warps instead (a_mbar_wait_guard): every deadlock of this kernel also blocks the TMA and the MMA warp, whose
+// bounded waits then trap — a pipeline bug still surfaces as a launch failure, never as a hung GPU.
 __device__ __forceinline__ void a_mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = a_smem_u32(bar);
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void a_mbar_wait_guard(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = a_smem_u32(bar);
   uint32_t ok, spins = 0;
   long long t0 = 0;
@@ -297,7 +311,7 @@ __global__ void __launch_bounds__(AT_THREADS, (D <= 32) ? 2 : 1) k_attn_tc(const
       __syncwarp();
       int stage = 0; uint32_t phase = 0;
       for (int j = 0; j < nblk; ++j) {
-        a_mbar_wait(&bar_empty[stage], phase ^ 1u);
+        a_mbar_wait_guard(&bar_empty[stage], phase ^ 1u);
         if (a_elect_one()) {
           a_mbar_expect_tx(&bar_full[stage], SM::STAGE_TX);
           const uint32_t sK_hi = sStage0 + stage * SM::STAGE, sK_lo = sK_hi + SM::K_SLOT;
@@ -313,7 +327,7 @@ __global__ void __launch_bounds__(AT_THREADS, (D <= 32) ? 2 : 1) k_attn_tc(const
         if (++stage == AT_NS) { stage = 0; phase ^= 1u; }
       }
     }
-    a_mbar_wait(&bar_pv_done[(nblk - 1) & 1], last_pv_par);   // all threads trigger when only the epilogue remains
+    a_mbar_wait_guard(&bar_pv_done[(nblk - 1) & 1], last_pv_par);   // all threads trigger when only the epilogue remains
     MTV_PDL_TRIGGER();
     if (kvs > 1) a_cluster_sync();
   } else if (warp == 1) {
@@ -337,8 +351,8 @@ __global__ void __launch_bounds__(AT_THREADS, (D <= 32) ? 2 : 1) k_attn_tc(const
         }
         __syncwarp();
       };
-      a_mbar_wait(&bar_q, 0);
-      a_mbar_wait(&bar_full[0], 0);
+      a_mbar_wait_guard(&bar_q, 0);
+      a_mbar_wait_guard(&bar_full[0], 0);
       a_fence_after();
       issue_S(0);
       int stage = 0; uint32_t phase = 0;
@@ -346,12 +360,12 @@ __global__ void __launch_bounds__(AT_THREADS, (D <= 32) ? 2 : 1) k_attn_tc(const
         int nstage = stage + 1; uint32_t nphase = phase;
         if (nstage == AT_NS) { nstage = 0; nphase ^= 1u; }
         if (j + 1 < nblk) {
-          a_mbar_wait(&bar_full[nstage], nphase);
-          a_mbar_wait(&bar_s_free, (uint32_t)(j & 1));      // softmax has read S(j) out of TMEM
+          a_mbar_wait_guard(&bar_full[nstage], nphase);
+          a_mbar_wait_guard(&bar_s_free, (uint32_t)(j & 1));      // softmax has read S(j) out of TMEM
           a_fence_after();
           issue_S(nstage);
         }
-        a_mbar_wait(&bar_p_full[j & 1], (uint32_t)((j >> 1) & 1));   // P(j) is in tensor memory (and every correction of O is done)
+        a_mbar_wait_guard(&bar_p_full[j & 1], (uint32_t)((j >> 1) & 1));   // P(j) is in tensor memory (and every correction of O is done)
         a_fence_after();
         const uint32_t sV_hi = sStage0 + stage * SM::STAGE + 2 * SM::K_SLOT, sV_lo = sV_hi + SM::V_SLOT;
         const uint64_t vh0 = dPV + off16(sV_hi), vl0 = dPV + off16(sV_lo);
@@ -376,7 +390,7 @@ __global__ void __launch_bounds__(AT_THREADS, (D <= 32) ? 2 : 1) k_attn_tc(const
         stage = nstage; phase = nphase;
       }
     }
-    a_mbar_wait(&bar_pv_done[(nblk - 1) & 1], last_pv_par);
+    a_mbar_wait_guard(&bar_pv_done[(nblk - 1) & 1], last_pv_par);
     MTV_PDL_TRIGGER();
     if (kvs > 1) a_cluster_sync();
   } else {

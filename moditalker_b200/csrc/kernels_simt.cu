@@ -13,7 +13,7 @@
 
 namespace mtv {
 
-int g_mtv_use_pdl = [] { const char* e = getenv("MTV_PDL"); return e ? atoi(e) : 5; }();
+int g_mtv_use_pdl = [] { const char* e = getenv("MTV_PDL"); return e ? atoi(e) : 7; }();
 
 // ------------------------------------------------------------------ token geometry
 __device__ __forceinline__ void decode_tok(const Geo& g, int tok, int& p, int& y, int& x) {

@@ -316,8 +316,22 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-// Bounded: a pipeline bug must surface as a launch failure (trap), never as a hung GPU.
+// Bare retry loop for the hot waits (MMA issuer, epilogue): extra instructions in it are not free (kernels_attn_tc.cu).  The hang
+// guard lives in the TMA producer warp (mbar_wait_guard): every deadlock of this kernel also blocks that warp (it waits for ring
+// slots and, at the end, for the accumulator), whose bounded wait then traps — a pipeline bug surfaces as a launch failure, never
+// as a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void mbar_wait_guard(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   uint32_t ok, spins = 0;
   long long t0 = 0;
@@ -1064,7 +1078,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
       MTV_PDL_WAIT();                // ... the activation operand does
       int stage = 0; uint32_t phase = 0;
       for (int it = it0; it < it1; ++it) {
-        if (it - it0 >= npre) mbar_wait(&bar_empty[stage], phase ^ 1u);
+        if (it - it0 >= npre) mbar_wait_guard(&bar_empty[stage], phase ^ 1u);
         if (elect_one()) {
           if (it - it0 >= npre) {
             mbar_expect_tx(&bar_full[stage], TX_BYTES);
@@ -1079,7 +1093,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
     // Dependents may be scheduled once the accumulator is complete: only this CTA's epilogue remains, so
     // the next kernel's launch latency and prologue overlap it without piling up many kernels deep.  Every
     // thread of the CTA triggers at that same point (the instruction's per-CTA semantics are not relied on).
-    mbar_wait(&bar_acc, 0);
+    mbar_wait_guard(&bar_acc, 0);
     MTV_PDL_TRIGGER();
   } else if (warp == 1) {
     // =============================== MMA issuer =================================

@@ -588,10 +588,15 @@ struct Builder {
     // vs ~1000 cycles for twice the work, profiles/r01_s2_mainloop_skip.md): take it once the SMs are covered, or whenever the
     // op is deep enough for split-K to restore the CTA count
     const int iters_all = S.taps * ((S.C0 + S.C1) / 64) + (P.nsegs == 2 ? (P.seg[1].C0 + P.seg[1].C1) / 64 : 0);
+    // split-K thresholds (K-iterations of 64 channels): ops with at least ks_min_total iterations are split so that every CTA
+    // keeps at least ks_min_it of them.  The reduction runs inside the GEMM kernel (no second launch), so fine splits pay:
+    // measured on B200 at B=1: min_it 3 -> 2.079 ms, 2 -> 2.054 ms
+    static const int ks_min_total = [] { const char* e = getenv("MTV_KS_MIN_TOTAL"); return e ? std::max(2, atoi(e)) : 16; }();
+    static const int min_it = [] { const char* e = getenv("MTV_KS_MIN_ITERS"); return e ? std::max(1, atoi(e)) : 2; }();
     int bn = 64;
     if (P.Cout % 128 == 0) {
       const int base128 = mtiles * (P.Cout / 128);
-      const bool splittable = iters_all >= 16 && ((h->tc_mask >> 5) & 1) && !o.qkv && base128 * 2 <= h->num_sms + h->num_sms / 4;
+      const bool splittable = iters_all >= ks_min_total && ((h->tc_mask >> 5) & 1) && !o.qkv && base128 * 2 <= h->num_sms + h->num_sms / 4;
       if (base128 >= 64 || (splittable && ((h->tc_mask >> 15) & 1))) bn = 128;
     }
     T.bn = bn;
@@ -623,10 +628,9 @@ struct Builder {
     const int iters = T.taps * (T.Cin / 64) + T.Cin2 / 64;
     const int base = mtiles * (P.Cout / bn);
     int ks = 1;
-    if (iters >= 16 && ((h->tc_mask >> 5) & 1) && !o.qkv && base * 2 <= h->num_sms + h->num_sms / 4) {
+    if (iters >= ks_min_total && ((h->tc_mask >> 5) & 1) && !o.qkv && base * 2 <= h->num_sms + h->num_sms / 4) {
       // spread a fixed amount of shared-memory / weight traffic over (nearly) all SMs; >= 3 K-iterations per CTA.  The ksplit CTAs
       // of an output tile wait for each other inside the kernel (tile ticket), so the whole grid must be co-resident: base*ks <= #SMs
-      static const int min_it = [] { const char* e = getenv("MTV_KS_MIN_ITERS"); return e ? std::max(1, atoi(e)) : 3; }();
       ks = std::min(iters / min_it, std::max(1, h->num_sms / base));
       ks = std::min(ks, 32);
       while (ks > 1 && (ks - 1) * ((iters + ks - 1) / ks) >= iters) --ks;
@@ -1081,7 +1085,10 @@ int mtv_create(const MtvConfig* cfg, MtvHandle* out) {
     const char* ng = getenv("MTV_NO_GRAPH");
     h->use_graph = !(ng && ng[0] == '1');
     if (const char* tm = getenv("MTV_TC_MASK")) h->tc_mask = (int)strtol(tm, nullptr, 0);
-    // programmatic dependent launch by kernel class: process-wide MTV_PDL mask read once at library load (mtv_kernels.cuh)
+    // programmatic dependent launch by kernel class (mtv_kernels.cuh): ONE process-wide mask, default 7 (tap-GEMM + attention +
+    // apply; measured on B200, B=1: 5 -> 2.120 ms, 7 / 15 / 31 -> 2.078 ms).  An MTV_PDL set in the environment at create time
+    // overrides it for the whole process (diagnostics / tests); handles do not carry their own mask.
+    if (const char* np = getenv("MTV_PDL")) g_mtv_use_pdl = atoi(np);
     register_weights(h.get());
     *out = h.release();
   });

@@ -119,10 +119,11 @@ class DDPM(nn.Module):
         self.first_stage_model = first_stage_model
         # test hook: noise_fn(kind, like_or_shape, device) -> tensor; default = torch.randn*
         self.noise_fn: Optional[Callable] = None
-        # host copies of the schedule (the reference indexes device buffers with Python ints)
-        self._host = {k: getattr(self, k).clone() for k in
-                      ("alphas_cumprod", "sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod",
-                       "sqrt_alphas_cumprod", "sqrt_one_minus_alphas_cumprod")}
+        # host copies of the schedule (the reference indexes the registered device buffers with Python ints; the fused step
+        # takes host scalars).  Refreshed whenever a buffer has been replaced or edited (load_state_dict, .to(), in-place
+        # writes): see _host_schedule().
+        self._host = None
+        self._host_key = None
 
     # ------------------------------------------------------------------ helpers
     def _unet(self) -> UNetModel:
@@ -143,6 +144,18 @@ class DDPM(nn.Module):
             return self.noise_fn("randn_like", tuple(ref.shape), ref.device)
         return torch.randn_like(ref)
 
+    _HOST_KEYS = ("alphas_cumprod", "sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod",
+                  "sqrt_alphas_cumprod", "sqrt_one_minus_alphas_cumprod")
+
+    def _host_schedule(self):
+        """CPU copies of the live schedule buffers, re-taken when any of them changed identity or content version
+        (``Tensor._version`` counts in-place edits; ``load_state_dict`` copies in place, ``.to()`` replaces the tensor)."""
+        key = tuple((getattr(self, k).data_ptr(), getattr(self, k)._version, str(getattr(self, k).device)) for k in self._HOST_KEYS)
+        if self._host is None or key != self._host_key:
+            self._host = {k: getattr(self, k).detach().to("cpu", copy=True) for k in self._HOST_KEYS}
+            self._host_key = key
+        return self._host
+
     def time_pairs(self):
         """ddpm.py:372-376."""
         times = torch.linspace(-1, self.num_timesteps - 1, steps=self.sampling_timesteps + 1)
@@ -153,7 +166,7 @@ class DDPM(nn.Module):
         """(sqrt_recip_ac, sqrt_recipm1_ac, sqrt(alpha_next), c, sigma) as Python floats
         holding exact fp32 values, computed with the reference's fp32 tensor ops
         (ddpm.py:280-281, 390-394)."""
-        H = self._host
+        H = self._host_schedule()
         sr = float(H["sqrt_recip_alphas_cumprod"][time])
         srm1 = float(H["sqrt_recipm1_alphas_cumprod"][time])
         if time_next < 0:
@@ -186,8 +199,9 @@ class DDPM(nn.Module):
             b = self.sqrt_one_minus_alphas_cumprod.gather(-1, t).reshape(-1, *((1,) * (x_start.dim() - 1)))
             return a * x_start + b * noise
         ti = int(t.reshape(-1)[0])
-        a = float(self._host["sqrt_alphas_cumprod"][ti])
-        b = float(self._host["sqrt_one_minus_alphas_cumprod"][ti])
+        H = self._host_schedule()
+        a = float(H["sqrt_alphas_cumprod"][ti])
+        b = float(H["sqrt_one_minus_alphas_cumprod"][ti])
         lib, h = self._unet()._ensure_engine(x_start.device)
         xs = x_start.detach().float().contiguous()
         nz = noise.detach().float().contiguous()

@@ -40,6 +40,22 @@ def test_time_pairs_and_scalars(S):
         assert torch.equal(mine, ddim_update(img, eps, nz, s, time, tn))   # bit-identical host scalars
 
 
+def test_step_scalars_follow_the_live_schedule_buffers():
+    """the fused step takes host scalars; they must track the registered buffers the reference indexes
+    (losses/ddpm.py:390-394), also after load_state_dict / in-place edits."""
+    d = _ddpm(50)
+    t, tn = d.time_pairs()[10]
+    before = d.step_scalars(t, tn)
+    other = DDPM(DiffusionWrapper(UNetModel(**TINY_UNET_CONFIG)), channels=4, image_size=32, sampling_timesteps=50, w=0.0,
+                 linear_start=0.0008, linear_end=0.012)
+    d.load_state_dict(other.state_dict())                       # a checkpoint trained with another beta schedule
+    after = d.step_scalars(t, tn)
+    assert after == other.step_scalars(t, tn) and after != before
+    with torch.no_grad():
+        d.alphas_cumprod.mul_(0.5)                              # in-place edit of a live buffer
+    assert d.step_scalars(t, tn) != after
+
+
 def test_sampler_rejects_foreign_model_and_ddpm_mode():
     d = DDPM(torch.nn.Identity(), channels=4, sampling_timesteps=10)
     with pytest.raises(TypeError):
