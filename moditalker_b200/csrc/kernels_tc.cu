@@ -793,17 +793,30 @@ __device__ __forceinline__ void tc_epilogue(const TcConvParams& P, const Geo& g,
         float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
         if (mine) {
           const float* src = pbase + ((size_t)(q * (BN / 32) + (u >> 3)) * 8 + (u & 7)) * 128 + lane * 4;
+          // the reduction is a chain of L2 round trips (~600 cycles each), not arithmetic: 16 independent loads per trip, summed
+          // in a fixed order (z ascending) whatever the trip size
           int z = 0;
-          for (; z + 4 <= ks; z += 4) {           // 4 independent loads in flight, fixed summation order
-            float4 v[4];
+          for (; z + 16 <= ks; z += 16) {
+            float4 v[16];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) v[i] = __ldcg(reinterpret_cast<const float4*>(src + (size_t)(z + i) * (TC_BM * BN)));
+            for (int i = 0; i < 16; ++i) v[i] = __ldcg(reinterpret_cast<const float4*>(src + (size_t)(z + i) * (TC_BM * BN)));
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { s.x += v[i].x; s.y += v[i].y; s.z += v[i].z; s.w += v[i].w; }
+            for (int i = 0; i < 16; ++i) { s.x += v[i].x; s.y += v[i].y; s.z += v[i].z; s.w += v[i].w; }
           }
-          for (; z < ks; ++z) {
-            const float4 v = __ldcg(reinterpret_cast<const float4*>(src + (size_t)z * (TC_BM * BN)));
-            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+          if (z + 8 <= ks) {
+            float4 v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = __ldcg(reinterpret_cast<const float4*>(src + (size_t)(z + i) * (TC_BM * BN)));
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { s.x += v[i].x; s.y += v[i].y; s.z += v[i].z; s.w += v[i].w; }
+            z += 8;
+          }
+          {
+            float4 v[8];                        // the last < 8 partials in one trip as well
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = (z + i < ks) ? __ldcg(reinterpret_cast<const float4*>(src + (size_t)(z + i) * (TC_BM * BN))) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) if (z + i < ks) { s.x += v[i].x; s.y += v[i].y; s.z += v[i].z; s.w += v[i].w; }
           }
           if (live) {
             const float4 ad = ps == 0 ? add0 : tc_bias_resid4(P, g, m, n0 + 4 * u, b, p, y, x);

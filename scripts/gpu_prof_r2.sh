@@ -17,7 +17,7 @@ for b in 1 8; do
 done
 # whole-step DRAM traffic without serialising the kernels: range replay around ONE step (graph launch + ddim step)
 for b in 1 8; do
-  timeout 600 ncu --replay-mode range --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none --cache-control none \
+  env MTV_NO_GRAPH=1 timeout 600 ncu --replay-mode range --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none --cache-control none \
       --csv --log-file $O/range_b${b}.csv python scripts/step_traffic.py $b > $O/range_b${b}.log 2>&1
   echo "ncu range b$b rc=$?" | tee -a $O/summary.txt
 done
