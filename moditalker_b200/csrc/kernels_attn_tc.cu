@@ -272,6 +272,9 @@ __global__ void __launch_bounds__(AT_THREADS, (D <= 32) ? 2 : 1) k_attn_tc(const
   const int bh = blockIdx.y;
   const int t_lo = P.seg_off[sg], len = P.seg_off[sg + 1] - t_lo;
   const int q0 = qb * AT_BQ;
+  // distributed shared memory of a peer may only be touched once that CTA is known to be executing: every thread arrives at
+  // the cluster barrier here and completes the wait (long since satisfied, no stall) right before the hand-over at the end
+  if (kvs > 1) asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   const int nblk_seg = (len + AT_BKV - 1) / AT_BKV;
   const int jb0 = (kr * nblk_seg) / kvs;                       // first key block of this rank
   const int nblk = ((kr + 1) * nblk_seg) / kvs - jb0;          // host guarantees >= 1
@@ -329,7 +332,7 @@ __global__ void __launch_bounds__(AT_THREADS, (D <= 32) ? 2 : 1) k_attn_tc(const
     }
     a_mbar_wait_guard(&bar_pv_done[(nblk - 1) & 1], last_pv_par);   // all threads trigger when only the epilogue remains
     MTV_PDL_TRIGGER();
-    if (kvs > 1) a_cluster_sync();
+    if (kvs > 1) { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); a_cluster_sync(); }
   } else if (warp == 1) {
     // =============================== MMA issuer =================================
     // whole warp in the loop, one elected lane issues; descriptors = base descriptor + (byte offset >> 4)
@@ -392,7 +395,7 @@ __global__ void __launch_bounds__(AT_THREADS, (D <= 32) ? 2 : 1) k_attn_tc(const
     }
     a_mbar_wait_guard(&bar_pv_done[(nblk - 1) & 1], last_pv_par);
     MTV_PDL_TRIGGER();
-    if (kvs > 1) a_cluster_sync();
+    if (kvs > 1) { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); a_cluster_sync(); }
   } else {
     // =============================== softmax / epilogue ==========================
     // warps 2-5: key columns [0,32) of each S block and output columns [0, D/2);
@@ -545,6 +548,7 @@ __global__ void __launch_bounds__(AT_THREADS, (D <= 32) ? 2 : 1) k_attn_tc(const
       // partial results of ranks > 0 -> rank 0's merge buffer [rank - 1][row][D + 2] = O[D] | m | l (distributed shared memory)
       float* mbuf = reinterpret_cast<float*>(smem_raw + (smem0 - a_smem_u32(smem_raw)) + SM::TOTAL - 1024);
       constexpr int MW = D + 2;
+      asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");     // the start-of-kernel arrival: every peer CTA is running
       if (kr > 0) {
         const uint32_t local = a_smem_u32(mbuf + ((size_t)(kr - 1) * AT_BQ + row) * MW + half * DH);
         uint32_t remote;
