@@ -8,6 +8,7 @@
 // The tensor-core (tcgen05) versions of the two big contractions live in
 // kernels_tc.cu and are cross-checked against these in tests/test_kernels_gpu.py.
 #include "mtv_kernels.cuh"
+#include <cuda_bf16.h>
 #include <math.h>
 #include <stdlib.h>
 
@@ -609,7 +610,28 @@ __global__ void k_pack_in(const __grid_constant__ PackParams P) {
   else v = (tok < 1024) ? P.image_cond[((size_t)b * P.ci + (c - P.cx - P.cc)) * P.ic_len + tok] : 0.0f;
   P.out[i] = v;
 }
+// same gather, written as the split-bf16 A operand of the tensor-core stem conv, channels zero-padded to cpad (a K chunk of 64)
+__global__ void k_pack_in_split(const __grid_constant__ PackParams P) {
+  const int Ct = P.cx + P.cc + P.ci;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)P.B * 2048 * P.cpad) return;
+  const int c = (int)(i % P.cpad);
+  const int tok = (int)((i / P.cpad) % 2048);
+  const int b = (int)(i / ((size_t)P.cpad * 2048));
+  float v = 0.0f;
+  if (c < P.cx) v = P.x[((size_t)b * P.cx + c) * 2048 + tok];
+  else if (c < P.cx + P.cc) v = P.cond[((size_t)b * P.cc + (c - P.cx)) * 2048 + tok];
+  else if (c < Ct) v = (tok < 1024) ? P.image_cond[((size_t)b * P.ci + (c - P.cx - P.cc)) * P.ic_len + tok] : 0.0f;
+  const __nv_bfloat16 h = __float2bfloat16_rn(v);
+  reinterpret_cast<__nv_bfloat16*>(P.hi)[i] = h;
+  reinterpret_cast<__nv_bfloat16*>(P.lo)[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+}
 cudaError_t launch_pack_in(const PackParams& P, cudaStream_t s) {
+  if (P.hi) {
+    const size_t n = (size_t)P.B * 2048 * P.cpad;
+    k_pack_in_split<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(P);
+    return cudaGetLastError();
+  }
   const size_t n = (size_t)P.B * 2048 * (P.cx + P.cc + P.ci);
   k_pack_in<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(P);
   return cudaGetLastError();

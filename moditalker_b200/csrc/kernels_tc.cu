@@ -301,6 +301,24 @@ __global__ void k_repack_split_w(const float* __restrict__ src, __nv_bfloat16* _
   const __nv_bfloat16 h = __float2bfloat16_rn(v);
   hi[i] = h; lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
 }
+// same, zero-padded to [taps][CoutPad][CinPad] (stem conv: 16 input channels -> one 64-channel K chunk; head conv: 4 output
+// channels -> one 64-column tile)
+__global__ void k_repack_split_w_pad(const float* __restrict__ src, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                                     int Cout, int Cin, int CoutPad, int CinPad, int taps) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)CoutPad * CinPad * taps) return;
+  const int ci = (int)(i % CinPad);
+  const int co = (int)((i / CinPad) % CoutPad);
+  const int tp = (int)(i / ((size_t)CinPad * CoutPad));
+  const float v = (ci < Cin && co < Cout) ? src[((size_t)co * Cin + ci) * taps + tp] : 0.0f;
+  const __nv_bfloat16 h = __float2bfloat16_rn(v);
+  hi[i] = h; lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+cudaError_t launch_repack_split_w_pad(const float* src, void* hi, void* lo, int Cout, int Cin, int CoutPad, int CinPad, int taps, cudaStream_t s) {
+  const size_t n = (size_t)CoutPad * CinPad * taps;
+  k_repack_split_w_pad<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(src, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, Cout, Cin, CoutPad, CinPad, taps);
+  return cudaGetLastError();
+}
 cudaError_t launch_repack_split_w(const float* src, void* hi, void* lo, int Cout, int Cin, int taps, cudaStream_t s) {
   const size_t n = (size_t)Cout * Cin * taps;
   k_repack_split_w<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(src, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, Cout, Cin, taps);
@@ -862,7 +880,7 @@ __device__ __forceinline__ void tc_epilogue(const TcConvParams& P, const Geo& g,
     tc_fence_after();
     // bulk-store path: the tile's rows are consecutive rows of the output (always at the large levels; at the small ones
     // only when a tile is exactly one sample) and the op has an output map
-    const bool ts = EPI != 2 && P.tma_store && (!T.small || T.spt == 1);
+    const bool ts = EPI != 2 && EPI != 4 && P.tma_store && (!T.small || T.spt == 1);
     const int ts_row = (int)((size_t)T.b0 * g.L + T.tok0) + q * 32;
 #pragma unroll
     for (int k = 0; k < NCH; ++k) {
@@ -917,7 +935,14 @@ __device__ __forceinline__ void tc_epilogue(const TcConvParams& P, const Geo& g,
         }
         fv[j] = v.x; fv[j + 1] = v.y; fv[j + 2] = v.z; fv[j + 3] = v.w;
       }
-      if constexpr (EPI != 2) {
+      if constexpr (EPI == 4) {
+        // head conv (unet.py:971-975): only the first out_cvalid columns are real; eps is channel-major [B][cvalid][L] — for a fixed
+        // channel the 32 lanes of a warp write 32 consecutive tokens
+        if (c0 == 0 && live) {
+          for (int nn = 0; nn < P.out_cvalid; ++nn) P.out[((size_t)b * P.out_cvalid + nn) * g.L + tok] = fv[nn];
+        }
+      }
+      if constexpr (EPI != 2 && EPI != 4) {
         if (ts) tc_stage_row(sbase, lane, fv);
         if (ts) {      // warp-uniform: every row of a bulk-stored tile is live
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -973,7 +998,7 @@ __device__ __forceinline__ void tc_epilogue(const TcConvParams& P, const Geo& g,
         for (int j = 0; j < 32; ++j) rpre[j] = rnext[j];
       }
     }
-    if constexpr (EPI != 2) {
+    if constexpr (EPI != 2 && EPI != 4) {
       if (P.csum && !(P.dbg_skip & 4)) {
         TC_EPI_BAR();
         tc_write_slots<BN>(P, g, T, n0, s_cs, 0, BN, et);
@@ -987,7 +1012,8 @@ __device__ __forceinline__ void tc_epilogue(const TcConvParams& P, const Geo& g,
 // EPI selects the epilogue at compile time (the row-per-lane epilogue is instruction-issue bound, so the
 // paths a launch cannot take must not even be predicated off):
 //   0 split-K (partials + in-kernel reduction), 1 bias [+ same-geometry residual] [+ GroupNorm sums], 2 qkv operand split,
-//   3 residual through nearest-up / avg-pool geometry (up / down ResBlocks with identity skip)
+//   3 residual through nearest-up / avg-pool geometry (up / down ResBlocks with identity skip),
+//   4 head conv: channel-major output of the first out_cvalid columns (BN = 64 only)
 template <int BN, int EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant__ TcConvParams P) {
   constexpr int NS = tc_stages(BN);
@@ -1174,7 +1200,8 @@ cudaError_t launch_conv_tc(const TcConvParams& P, cudaStream_t s) {
   if (ks > 1 && !P.sync) return cudaErrorInvalidValue;       // in-kernel waits need the co-residency guarantee
   if (ks > 1 && (!P.partial || P.qkv_heads)) return cudaErrorInvalidValue;
   cudaError_t e = cudaSuccess;
-  const int epi = ks > 1 ? 0 : (P.qkv_heads ? 2 : ((P.resid && P.resid_mode != RS_NONE) ? 3 : 1));
+  const int epi = ks > 1 ? 0 : (P.qkv_heads ? 2 : (P.out_cvalid ? 4 : ((P.resid && P.resid_mode != RS_NONE) ? 3 : 1)));
+  if (epi == 4 && (BN != 64 || P.Cout != 64 || P.out_cvalid > 32)) return cudaErrorInvalidValue;
 #define MTV_TC_LAUNCH(BN_, EPI_)                                                                                   \
   do {                                                                                                             \
     e = cudaFuncSetAttribute(k_conv_tc<BN_, EPI_>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(BN_)); \
@@ -1184,7 +1211,7 @@ cudaError_t launch_conv_tc(const TcConvParams& P, cudaStream_t s) {
   } while (0)
   if (BN == 64) {
     switch (epi) { case 0: MTV_TC_LAUNCH(64, 0); break; case 1: MTV_TC_LAUNCH(64, 1); break;
-                   case 2: MTV_TC_LAUNCH(64, 2); break; default: MTV_TC_LAUNCH(64, 3); break; }
+                   case 2: MTV_TC_LAUNCH(64, 2); break; case 4: MTV_TC_LAUNCH(64, 4); break; default: MTV_TC_LAUNCH(64, 3); break; }
   } else {
     switch (epi) { case 0: MTV_TC_LAUNCH(128, 0); break; case 1: MTV_TC_LAUNCH(128, 1); break;
                    case 2: MTV_TC_LAUNCH(128, 2); break; default: MTV_TC_LAUNCH(128, 3); break; }

@@ -116,6 +116,8 @@ struct PackParams {
   const float* x; const float* cond; const float* image_cond; int64_t ic_len;
   int B; int cx, cc, ci;                  // channel counts (4, 8, 4)
   float* out;                             // [B][2048][cx+cc+ci]
+  // tensor-core stem: instead of fp32 `out`, the split-bf16 operand [B][2048][cpad] (channels >= cx+cc+ci are zero)
+  void* hi; void* lo; int cpad;
 };
 
 // ---- launchers (kernels_simt.cu) ----

@@ -118,6 +118,7 @@ struct Weight {
   std::string name; std::vector<int64_t> shape; size_t elems = 0;
   float* dev = nullptr; bool owned = true; bool loaded = false; int kind = WK_PLAIN;
   void* hi = nullptr; void* lo = nullptr;   // split-bf16 K-major copy [taps][Cout][Cin] for the tcgen05 path
+  int pad_cin = 0, pad_cout = 0;            // > 0: the split copy is zero-padded to this many input (stem) / output (head) channels
 };
 
 struct Tensor {
@@ -158,6 +159,7 @@ struct MtvHandle_t {
   std::vector<Weight> weights; std::unordered_map<std::string, int> windex;
   std::vector<void*> allocs;
   float* emb_wall = nullptr; float* emb_ball = nullptr; float* freqs = nullptr;
+  float* head_bias_pad = nullptr;    // out.2.bias zero-padded to 64 (tensor-core head conv)
   std::unordered_map<std::string, float*> bias_sum;   // ResBlock name -> conv2.bias + skip.bias
   std::unordered_map<const float*, std::pair<void*, void*>> tc_w;   // fp32 conv weight -> split-bf16 pair
   bool dirty = true; bool use_graph = true;
@@ -171,7 +173,8 @@ struct MtvHandle_t {
   // bit 17 fused GroupNorm + qkv into the attention kernel as a cluster front end: all measured slower on B200 and removed —
   // profiles/r01_s2_chain_experiment.md, r01_s2_direct_experiment.md, r02_fused_apply_experiment.md,
   // r02_fused_attention_experiment.md.)
-  int tc_mask = 0x1cfff;
+  // 18 stem conv on the tensor cores (input channels padded 16 -> 64; its channel sums replace two k_gn_stats launches)
+  int tc_mask = 0x5cfff;
   cudaStream_t cap_stream = nullptr;
   cudaStream_t capture_stream() {
     if (!cap_stream) CK(cudaStreamCreateWithFlags(&cap_stream, cudaStreamNonBlocking));
@@ -230,6 +233,16 @@ struct MtvHandle_t {
     }
     if (kind == WK_CONV && cfg.kernel_path != 1 && shape[0] % 64 == 0 && shape[1] % 64 == 0) {
       w.hi = dalloc(w.elems * 2); w.lo = dalloc(w.elems * 2);
+      tc_w[w.dev] = std::make_pair(w.hi, w.lo);
+    } else if (kind == WK_CONV && cfg.kernel_path != 1 && name == "input_blocks.0.0.weight" && shape[0] % 64 == 0 && shape[1] < 64) {
+      // stem conv on the tensor cores: its 4*in_channels input channels are zero-padded to one 64-channel K chunk
+      const size_t padded = w.elems / (size_t)shape[1] * 64;
+      w.hi = dalloc(padded * 2); w.lo = dalloc(padded * 2); w.pad_cin = 64;
+      tc_w[w.dev] = std::make_pair(w.hi, w.lo);
+    } else if (kind == WK_CONV && cfg.kernel_path != 1 && name == "out.2.weight" && shape[0] < 64 && shape[1] % 64 == 0) {
+      // head conv on the tensor cores: its out_channels output channels are zero-padded to one 64-column tile
+      const size_t padded = w.elems / (size_t)shape[0] * 64;
+      w.hi = dalloc(padded * 2); w.lo = dalloc(padded * 2); w.pad_cout = 64;
       tc_w[w.dev] = std::make_pair(w.hi, w.lo);
     }
     weight_bytes += (int64_t)w.elems * 4;
@@ -307,6 +320,10 @@ void register_weights(MtvHandle_t* h) {
   h->add_weight("out.0.bias", {A.head_ch}, WK_PLAIN);
   h->add_weight("out.2.weight", {c.out_channels, mc, 3, 3}, WK_CONV);
   h->add_weight("out.2.bias", {c.out_channels}, WK_PLAIN);
+  if (c.kernel_path != 1 && c.out_channels < 64) {
+    h->head_bias_pad = h->dalloc(64 * sizeof(float));
+    CK(cudaMemset(h->head_bias_pad, 0, 64 * sizeof(float)));
+  }
 
   // timestep_embedding frequencies, fp32 like the reference (diffusionmodules.py:118-121)
   const int half = mc / 2;
@@ -326,6 +343,8 @@ void ensure_ready(MtvHandle_t* h, cudaStream_t s) {
     const int n = (int)h->weights[h->windex.at(p + ".out_layers.3.bias")].elems;
     CK(launch_add_vec(h->W(p + ".out_layers.3.bias"), h->W(p + ".skip_connection.bias"), kv.second, n, s));
   }
+  if (h->head_bias_pad)
+    CK(cudaMemcpyAsync(h->head_bias_pad, h->W("out.2.bias"), (size_t)h->cfg.out_channels * sizeof(float), cudaMemcpyDeviceToDevice, s));
   h->dirty = false;
 }
 
@@ -369,6 +388,7 @@ struct TcOpts {
   const SplitBuf* pre1 = nullptr;     // seg1 (skip) operand already exists
   SplitBuf* raw_out = nullptr;        // ask seg0's apply kernel to also emit the raw split of its source
   const QkvSplitParams* qkv = nullptr;  // qkv GEMM: epilogue writes the attention operands instead of fp32
+  int chmajor_valid = 0;              // head conv: channel-major output of the first chmajor_valid columns, no split-K
 };
 
 struct Builder {
@@ -596,7 +616,7 @@ struct Builder {
     int bn = 64;
     if (P.Cout % 128 == 0) {
       const int base128 = mtiles * (P.Cout / 128);
-      const bool splittable = iters_all >= ks_min_total && ((h->tc_mask >> 5) & 1) && !o.qkv && base128 * 2 <= h->num_sms + h->num_sms / 4;
+      const bool splittable = iters_all >= ks_min_total && ((h->tc_mask >> 5) & 1) && !o.qkv && !o.chmajor_valid && base128 * 2 <= h->num_sms + h->num_sms / 4;
       if (base128 >= 64 || (splittable && ((h->tc_mask >> 15) & 1))) bn = 128;
     }
     T.bn = bn;
@@ -628,7 +648,7 @@ struct Builder {
     const int iters = T.taps * (T.Cin / 64) + T.Cin2 / 64;
     const int base = mtiles * (P.Cout / bn);
     int ks = 1;
-    if (iters >= ks_min_total && ((h->tc_mask >> 5) & 1) && !o.qkv && base * 2 <= h->num_sms + h->num_sms / 4) {
+    if (iters >= ks_min_total && ((h->tc_mask >> 5) & 1) && !o.qkv && !o.chmajor_valid && base * 2 <= h->num_sms + h->num_sms / 4) {
       // spread a fixed amount of shared-memory / weight traffic over (nearly) all SMs; >= 3 K-iterations per CTA.  The ksplit CTAs
       // of an output tile wait for each other inside the kernel (tile ticket), so the whole grid must be co-resident: base*ks <= #SMs
       ks = std::min(iters / min_it, std::max(1, h->num_sms / base));
@@ -647,7 +667,8 @@ struct Builder {
     op.flops = 2.0 * M * P.Cout * Ktot;
     op.bytes = 4.0 * Ktot * P.Cout + 4.0 * M * Ktot / S.taps + 4.0 * M * P.Cout;
     if (const char* ds = getenv("MTV_TC_DBG_SKIP")) T.dbg_skip = atoi(ds);
-    if (!o.qkv && ks == 1 && ((h->tc_mask >> 16) & 1)) {      // epilogue tiles leave through TMA stores (kernels_tc.cu: tma_store_2d)
+    T.out_cvalid = o.chmajor_valid;
+    if (!o.qkv && !o.chmajor_valid && ks == 1 && ((h->tc_mask >> 16) & 1)) {      // epilogue tiles leave through TMA stores (kernels_tc.cu: tma_store_2d)
       const uint64_t dims[2] = {(uint64_t)P.Cout, (uint64_t)M}; const uint64_t str[1] = {(uint64_t)P.Cout * 4};
       const uint32_t box[2] = {32, 32};
       T.tmOut = make_tmap_bf16(T.out, 2, dims, str, box, 128, true);
@@ -898,9 +919,19 @@ struct Builder {
       };
       pl->ops.push_back(op);
     }
-    Tensor xin = T(4 * c.in_channels, 0);
+    // tensor-core stem (unet.py:714): the packed input is written directly as the split-bf16 operand, channels padded to 64
+    const bool tc_stem = c.kernel_path != 1 && (h->tc_mask & 1) && ((h->tc_mask >> 18) & 1) && mc % 64 == 0 && 4 * c.in_channels < 64 &&
+                         h->tc_w.count(h->W("input_blocks.0.0.weight"));
+    Tensor xin; SplitBuf xin_split;
+    if (tc_stem) {
+      const size_t bytes = (size_t)B * geo(0).L * 64 * 2;
+      xin_split.hi = dalloc(bytes); xin_split.lo = dalloc(bytes);
+    } else {
+      xin = T(4 * c.in_channels, 0);
+    }
     {
       PackParams P{}; P.B = B; P.cx = c.in_channels; P.cc = 2 * c.in_channels; P.ci = c.in_channels; P.out = xin.p;
+      P.hi = xin_split.hi; P.lo = xin_split.lo; P.cpad = 64;
       Op op; op.name = "pack_in"; op.phase = 0;
       op.fn = [plan, P](cudaStream_t s) {
         PackParams Q = P; Q.x = plan->ctx.x; Q.cond = plan->ctx.cond; Q.image_cond = plan->ctx.image_cond;
@@ -935,9 +966,10 @@ struct Builder {
     {
       cur = T(mc, 0);
       ConvParams P{}; P.nsegs = 1; P.geo = geo(0); P.Cout = mc;
-      KSeg& S = P.seg[0]; S.src0 = xin.p; S.C0 = xin.C; S.taps = 9; S.w = h->W("input_blocks.0.0.weight");
+      KSeg& S = P.seg[0]; S.src0 = xin.p; S.C0 = tc_stem ? 64 : xin.C; S.taps = 9; S.w = h->W("input_blocks.0.0.weight");
       P.bias = h->W("input_blocks.0.0.bias"); P.out = cur.p;
-      conv("input_blocks.0.0", P, -1, -1, &cur);
+      if (tc_stem) { P.B = B; TcOpts o; o.pre0 = &xin_split; conv_tc("input_blocks.0.0", P, -1, -1, &cur, o); }
+      else conv("input_blocks.0.0", P, -1, -1, &cur);
       pl->taps["in0"] = cur; skips.push_back(cur); keep.insert(cur.p);
     }
     for (size_t i = 1; i < A.in.size(); ++i) {
@@ -957,7 +989,15 @@ struct Builder {
     // ---- head: GN -> SiLU -> conv3x3 -> channel-major eps (unet.py:971-975, 1103-1112)
     const int nh = gn("out.0", cur, nullptr, false, h->W("out.0.weight"), h->W("out.0.bias"), -1);
     float* eps_buf = (float*)dalloc((size_t)B * c.out_channels * geo(0).L * sizeof(float));
-    {
+    const bool tc_head = c.kernel_path != 1 && (h->tc_mask & 1) && ((h->tc_mask >> 18) & 1) && cur.C % 64 == 0 && c.out_channels <= 32 &&
+                         h->head_bias_pad && h->tc_w.count(h->W("out.2.weight")) && cur.csum;
+    if (tc_head) {   // tensor-core head: Cout padded 4 -> 64, channel-major epilogue; GroupNorm + SiLU from the producer's channel sums
+      ConvParams P{}; P.nsegs = 1; P.geo = geo(0); P.Cout = 64; P.B = B;
+      KSeg& S = P.seg[0]; S.src0 = cur.p; S.C0 = cur.C; S.silu = 1; S.taps = 9; S.w = h->W("out.2.weight");
+      P.bias = h->head_bias_pad; P.out = eps_buf;
+      TcOpts o; o.chmajor_valid = c.out_channels;
+      conv_tc("out.2", P, nh, -1, nullptr, o);
+    } else {
       ConvParams P{}; P.nsegs = 1; P.geo = geo(0); P.Cout = c.out_channels;
       KSeg& S = P.seg[0]; S.src0 = cur.p; S.C0 = cur.C; S.silu = 1;
       S.taps = 9; S.w = h->W("out.2.weight");
@@ -1129,7 +1169,9 @@ int mtv_load_weight(MtvHandle h, const char* name, const float* data, const int6
       const int Cout = (int)w.shape[0], Cin = (int)w.shape[1];
       const int taps = (int)(w.elems / ((size_t)Cout * Cin));
       CK(launch_repack_conv(data, w.dev, Cout, Cin, taps, s));
-      if (w.hi) CK(launch_repack_split_w(data, w.hi, w.lo, Cout, Cin, taps, s));
+      if (w.hi && (w.pad_cin || w.pad_cout))
+        CK(launch_repack_split_w_pad(data, w.hi, w.lo, Cout, Cin, w.pad_cout ? w.pad_cout : Cout, w.pad_cin ? w.pad_cin : Cin, taps, s));
+      else if (w.hi) CK(launch_repack_split_w(data, w.hi, w.lo, Cout, Cin, taps, s));
     } else {
       CK(cudaMemcpyAsync(w.dev, data, w.elems * sizeof(float), cudaMemcpyDeviceToDevice, s));
     }

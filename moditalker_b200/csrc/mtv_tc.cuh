@@ -64,6 +64,7 @@ struct TcConvParams {
   int taps, Cin, Cout, B; Geo geo;
   const float* bias; const float* resid; int resid_mode;
   float* out; float* partial; int ksplit;
+  int out_cvalid;                     // > 0 (head conv): `out` is channel-major [B][out_cvalid][L] and only the first out_cvalid of the Cout = 64 columns are stored
   double* csum;                       // optional channel-sum slots of `out` (csum_at) for the next GroupNorm
   // split-K tickets (64-bit generation counters, never reset, zero once at allocation): word [tile * 32] belongs to output
   // tile `tile` = blockIdx.x * gridDim.y + blockIdx.y.  Required by ksplit > 1, which the host only selects for grids of at
@@ -103,6 +104,7 @@ cudaError_t launch_attn_tc(const AttnTcParams& P, cudaStream_t s);
 
 cudaError_t launch_apply_split(const ApplyParams& P, cudaStream_t s);
 cudaError_t launch_repack_split_w(const float* src, void* hi, void* lo, int Cout, int Cin, int taps, cudaStream_t s);
+cudaError_t launch_repack_split_w_pad(const float* src, void* hi, void* lo, int Cout, int Cin, int CoutPad, int CinPad, int taps, cudaStream_t s);
 cudaError_t launch_conv_tc(const TcConvParams& P, cudaStream_t s);
 cudaError_t tc_debug_arm(long long* buf, unsigned int cap);
 cudaError_t tc_debug_count(unsigned int* n);
