@@ -16,8 +16,17 @@
  *   - every tensor argument is a raw DEVICE pointer to contiguous fp32 (int64 for
  *     timesteps) owned by the caller (PyTorch); the library owns only its repacked
  *     weights and workspace, released by mtv_destroy
- *   - `stream` is a cudaStream_t passed as void*; all work is stream-ordered, no
- *     hidden device synchronisation in the forward / step calls
+ *   - `stream` is a cudaStream_t passed as void*; all work is stream-ordered.  The FIRST
+ *     mtv_unet_forward for a new batch size builds that batch size's launch plan (workspace
+ *     allocation, one cudaDeviceSynchronize; must not happen while the caller is capturing a
+ *     graph); at most four plans are cached, least recently used dropped.  Every later call
+ *     is free of host synchronisation
+ *   - caller state is left alone: every entry point restores the caller's current CUDA
+ *     device; the caller's stream never receives attributes (the L2 access-policy window is
+ *     set on a private capture stream only; the device-wide persisting-L2 limit is restored
+ *     by mtv_destroy)
+ *   - results are bit-reproducible for a given (weights, inputs, batch size): GroupNorm sums
+ *     and split-K reductions use fixed orders, no floating-point atomics
  *   - every function returns 0 on success, non-zero on error; mtv_last_error()
  *     returns a message for the calling thread's last failure.  No C++ exception
  *     crosses this boundary.
@@ -52,7 +61,7 @@ typedef struct MtvConfig {
   int32_t attn_at_level[MTV_MAX_LEVELS]; /* 1 if (1<<level) is in attention_resolutions */
   int32_t device;                 /* CUDA device ordinal */
   int32_t kernel_path;            /* 0 = default: tcgen05 tensor-core kernels (split-bf16, ~1e-5 vs fp32) for every
-                                         tap-GEMM and attention with a tile shape, fp32 CUDA-core kernels for stem / head,
+                                         tap-GEMM (stem and head included) and every attention with a tile shape,
                                      1 = fp32 CUDA-core kernels everywhere (cross-check path of the tests, ~1e-6) */
 } MtvConfig;
 
