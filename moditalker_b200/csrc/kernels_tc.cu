@@ -623,11 +623,7 @@ constexpr int TC_SYNC_STRIDE = 32;     // 64-bit words between two counters (256
 // Shared-memory carve-up of the (idle once the accumulator is complete) operand ring during the epilogue
 constexpr uint32_t TC_EPI_STAGE_OFF = 0;            // per (warp, chunk) staging tiles of 32 rows x 32 fp32, 128B-swizzled: <= 64 KB
 constexpr uint32_t TC_EPI_CS_OFF = 65536;           // float [16 row groups][BN][2]: channel sums per aligned group of 8 tile rows
-constexpr uint32_t TC_EPI_TBL_OFF = 65536 + 16384;  // float2 [<= 12 (sample, plane) pairs][BN]: fused-apply affine (a, d)
-constexpr uint32_t TC_EPI_ST_OFF = 65536 + 16384 + 12288;   // double2 [<= 12][<= 32 groups]: (mean, rstd)
-constexpr int TC_EPI_MAXG = 32;
-constexpr uint32_t TC_EPI_PRM_OFF = TC_EPI_ST_OFF + 12 * TC_EPI_MAXG * 16;   // float gamma[128] | beta[128] | FiLM scale[4][128] | shift[4][128]
-static_assert(TC_EPI_PRM_OFF + 10 * 128 * 4 <= 3 * tc_stage_bytes(128) && TC_EPI_PRM_OFF + 10 * 128 * 4 <= 4 * tc_stage_bytes(64), "epilogue scratch fits the ring");
+static_assert(TC_EPI_CS_OFF + 16384 <= 3 * tc_stage_bytes(128) && TC_EPI_CS_OFF + 16384 <= 4 * tc_stage_bytes(64), "epilogue scratch fits the ring");
 
 // (sum, sum of squares) of a 32-column chunk over each aligned group of 8 tile rows -> dst[row group][column][2] (floats;
 // `ld` floats between row groups).  8 rows never straddle a (sample, plane) boundary at any level (plane sizes are multiples of
@@ -694,83 +690,6 @@ __device__ __forceinline__ void tc_write_slots(const TcConvParams& P, const Geo&
   }
 }
 
-// Local fused consumer apply (small levels), part 1 — nothing here depends on this launch: gamma / beta / FiLM rows of tile columns
-// [c_lo, c_hi) -> shared memory, issued before the accumulator wait.
-__device__ __forceinline__ void tc_fa_prefetch(const TcConvParams& P, const TcTile& T, int n0, int c_lo, int c_hi, float* s_prm, int et) {
-  const FusedApply& F = P.fa;
-  const int ncol = c_hi - c_lo, C = P.Cout;
-  const int nsamp = min(T.spt, P.B - T.b0);
-  for (int i = et; i < ncol; i += 256) {
-    const int col = c_lo + i, c = n0 + col;
-    s_prm[col] = __ldg(F.gamma + c); s_prm[128 + col] = __ldg(F.beta + c);
-  }
-  if (F.film) {
-    for (int i = et; i < nsamp * ncol; i += 256) {
-      const int sm = i / ncol, col = c_lo + (i - sm * ncol), c = n0 + col;
-      const float* f = F.film + (size_t)(T.b0 + sm) * F.film_stride;
-      s_prm[256 + sm * 128 + col] = __ldg(f + c); s_prm[768 + sm * 128 + col] = __ldg(f + C + c);
-    }
-  }
-}
-// Part 2: s_cs holds (sum, sum of squares) of every aligned group of 8 tile rows for columns [c_lo, c_hi) — whole GroupNorm groups,
-// all rows of every sample of the tile — so the statistics are complete on chip: affine table tbl[sp][col] = (a, d), y = x*a + d, for
-// sp = sample_in_tile*3 + plane.  Same arithmetic as apply_norm_unit (fp64 statistics, fp32 result), same summation structure as the
-// slot path (8-row groups in order, then channels).
-template <int BN>
-__device__ __forceinline__ void tc_build_fa_table_local(const TcConvParams& P, const Geo& g, const TcTile& T, int n0, int c_lo, int c_hi,
-                                                        const float* s_cs, float2* tbl, double2* s_st, const float* s_prm, int et) {
-  const FusedApply& F = P.fa;
-  const int C = P.Cout, cpg = C / 32;
-  const int g_lo = (n0 + c_lo) / cpg, ng = (c_hi - c_lo) / cpg;
-  const int nsamp = min(T.spt, P.B - T.b0);
-  const int nsp = nsamp * 3;
-  const int npairs = nsp * ng;
-  for (int base = 0; base < npairs * 8; base += 256) {      // 8 lanes per (sp, group); whole warps in or out of the shuffles
-    const int idx = base + et;
-    const int pair = idx >> 3, l8 = idx & 7;
-    const bool act = pair < npairs;
-    const int sp = act ? pair / ng : 0, gi = act ? pair - sp * ng : 0;
-    const int sm = sp / 3, p = sp - sm * 3;
-    double s = 0.0, q = 0.0;
-    if (act) {
-      for (int ci = l8; ci < cpg; ci += 8) {
-        const int col = (g_lo + gi) * cpg + ci - n0;
-        for (int pp = F.joint ? 0 : p; pp < (F.joint ? 3 : p + 1); ++pp) {
-          int r0, nr; tc_small_rows(T, sm, pp, r0, nr);
-          for (int rg = r0 >> 3; rg < ((r0 + nr) >> 3); ++rg) {
-            const float2 v = *reinterpret_cast<const float2*>(s_cs + ((size_t)rg * BN + col) * 2);
-            s += (double)v.x; q += (double)v.y;
-          }
-        }
-      }
-    }
-#pragma unroll
-    for (int off = 4; off > 0; off >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, off); q += __shfl_xor_sync(0xffffffffu, q, off); }
-    if (act && l8 == 0) {
-      const double cnt = (double)cpg * (F.joint ? (double)g.L : (double)(p == 0 ? T.nxy : T.npl));
-      const double mean = s / cnt;
-      double var = q / cnt - mean * mean; var = var < 0.0 ? 0.0 : var;
-      s_st[sp * TC_EPI_MAXG + gi] = make_double2(mean, rsqrt(var + 1e-5));
-    }
-  }
-  TC_EPI_BAR();
-  const int ncol = c_hi - c_lo;
-  for (int i = et; i < nsp * ncol; i += 256) {
-    const int sp = i / ncol, col = c_lo + (i - sp * ncol);
-    const int c = n0 + col;
-    const int sm = sp / 3;
-    const double2 st = s_st[sp * TC_EPI_MAXG + (c / cpg - g_lo)];
-    double a = st.y * (double)s_prm[col];
-    double d = (double)s_prm[128 + col] - st.x * a;
-    if (F.film) {
-      const double sc = 1.0 + (double)s_prm[256 + sm * 128 + col];
-      a *= sc; d = d * sc + (double)s_prm[768 + sm * 128 + col];
-    }
-    tbl[sp * BN + col] = make_float2((float)a, (float)d);
-  }
-  TC_EPI_BAR();
-}
-
 __device__ __forceinline__ uint32_t tc_cvt_bf16x2(float lo_elem, float hi_elem) {
   uint32_t r;
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
@@ -832,14 +751,7 @@ __device__ __forceinline__ void tc_epilogue(const TcConvParams& P, const Geo& g,
   int b, tok; tc_row_map(T, row, b, tok);
   const bool live = b < P.B;
   const size_t m = (size_t)b * g.L + tok;
-  int p = 0, y = 0, x = 0;
-  tc_decode_fast(T, tok, p, y, x);
-  const int p_of_row = p;
   float* s_cs = reinterpret_cast<float*>(ring + TC_EPI_CS_OFF);
-  float2* s_tbl = reinterpret_cast<float2*>(ring + TC_EPI_TBL_OFF);
-  double2* s_st = reinterpret_cast<double2*>(ring + TC_EPI_ST_OFF);
-  float* s_prm = reinterpret_cast<float*>(ring + TC_EPI_PRM_OFF);
-  const int sp_row = T.small ? (b - T.b0) * 3 + p_of_row : 0;
   unsigned long long* sync = P.sync;
   MTV_PDL_WAIT();                               // residual / statistics buffers belong to earlier kernels
   unsigned long long tgt_tile = 0;
@@ -851,23 +763,16 @@ __device__ __forceinline__ void tc_epilogue(const TcConvParams& P, const Geo& g,
     if (et < BN) s_bias[et] = P.bias ? __ldg(P.bias + n0 + et) : 0.0f;
     TC_EPI_BAR();
   }
+  int p = 0, y = 0, x = 0;
+  tc_decode_fast(T, tok, p, y, x);
   
   if constexpr (EPI == 0) {
     // ---------------------------------------------------------------- split-K
     const int ks = P.ksplit;
     const int tile_id = blockIdx.x * gridDim.y + blockIdx.y;
     constexpr int U = BN / 4;                   // reduction units of a tile: 4 columns x 128 rows (one warp per row quarter)
-    // this CTA's contiguous share of the units; whole GroupNorm groups (cpg/4 units each) when the consumer's apply is fused,
-    // so that the statistics of its columns are complete on chip (host: small level, cpg % 4 == 0, BN % cpg == 0)
-    int u0, u1;
-    if (P.fa.hi) {
-      const int upg = (P.Cout / 32) / 4, G = U / upg;
-      u0 = ((zidx * G) / ks) * upg; u1 = (((zidx + 1) * G) / ks) * upg;
-    } else {
-      u0 = (zidx * U) / ks; u1 = ((zidx + 1) * U) / ks;
-    }
+    const int u0 = (zidx * U) / ks, u1 = ((zidx + 1) * U) / ks;     // this CTA's contiguous share
     constexpr int MAXPASS = U / 4;              // ks >= 2 -> <= U/2 units per CTA, two units (warp groups) per pass
-    if (P.fa.hi && u1 > u0) tc_fa_prefetch(P, T, n0, 4 * u0, 4 * u1, s_prm, et);
     float4 add0 = make_float4(0.f, 0.f, 0.f, 0.f);
     if (live && u0 + wg < u1) add0 = tc_bias_resid4(P, g, m, n0 + 4 * (u0 + wg), b, p, y, x);   // first pass: fetched under the main loop
     mbar_wait(bar_acc, 0);
@@ -958,31 +863,11 @@ __device__ __forceinline__ void tc_epilogue(const TcConvParams& P, const Geo& g,
       TC_EPI_BAR();
       if (u1 > u0) tc_write_slots<BN>(P, g, T, n0, s_cs, 4 * u0, 4 * u1, et);
     }
-    if (P.fa.hi && u1 > u0) {                     // CTA-uniform; the sums of [4u0, 4u1) x all rows are in s_cs (barrier above)
-      tc_build_fa_table_local<BN>(P, g, T, n0, 4 * u0, 4 * u1, s_cs, s_tbl, s_st, s_prm, et);
-#pragma unroll
-      for (int ps = 0; ps < MAXPASS; ++ps) {
-        const int u = u0 + 2 * ps + wg;
-        if (u < u1 && live) {
-          const float4 ad0 = *reinterpret_cast<const float4*>(s_tbl + sp_row * BN + 4 * u);
-          const float4 ad1 = *reinterpret_cast<const float4*>(s_tbl + sp_row * BN + 4 * u + 2);
-          float y0 = fmaf(val[ps].x, ad0.x, ad0.y), y1 = fmaf(val[ps].y, ad0.z, ad0.w);
-          float y2 = fmaf(val[ps].z, ad1.x, ad1.y), y3 = fmaf(val[ps].w, ad1.z, ad1.w);
-          if (P.fa.silu) { y0 = silu_tc(y0); y1 = silu_tc(y1); y2 = silu_tc(y2); y3 = silu_tc(y3); }
-          uint2 hi, lo;
-          tc_split2(y0, y1, hi.x, lo.x); tc_split2(y2, y3, hi.y, lo.y);
-          const size_t o = m * P.Cout + n0 + 4 * u;
-          *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(P.fa.hi) + o) = hi;
-          *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(P.fa.lo) + o) = lo;
-        }
-      }
-    }
     if (stamp && threadIdx.x == 64) stamp[7] = clock64();
     return;
   } else {
     // ---------------------------------------------------------------- one CTA owns the whole K range
     // the residual of the first 32-column chunk is fetched while the MMAs still run
-    if (EPI != 2 && EPI != 4 && P.fa.hi) tc_fa_prefetch(P, T, n0, 0, BN, s_prm, et);
     const bool pre_res = EPI == 1 && live && P.resid;
     float rpre[32];
     if (pre_res) {
@@ -1060,7 +945,7 @@ __device__ __forceinline__ void tc_epilogue(const TcConvParams& P, const Geo& g,
         }
       }
       if constexpr (EPI != 2 && EPI != 4) {
-        if (ts || P.fa.hi) tc_stage_row(sbase, lane, fv);   // staged: bulk-store source and / or the fused apply's input
+        if (ts) tc_stage_row(sbase, lane, fv);
         if (ts) {      // warp-uniform: every row of a bulk-stored tile is live
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
@@ -1119,34 +1004,6 @@ __device__ __forceinline__ void tc_epilogue(const TcConvParams& P, const Geo& g,
       if (P.csum && !(P.dbg_skip & 4)) {
         TC_EPI_BAR();
         tc_write_slots<BN>(P, g, T, n0, s_cs, 0, BN, et);
-      }
-      if (P.fa.hi) {                              // small level: this CTA holds every row of its samples for its BN columns
-        tc_build_fa_table_local<BN>(P, g, T, n0, 0, BN, s_cs, s_tbl, s_st, s_prm, et);
-#pragma unroll
-        for (int k = 0; k < NCH; ++k) {
-          const int c0 = (wg + 2 * k) * 32;
-          const uint32_t sbase = ring_u32 + TC_EPI_STAGE_OFF + (uint32_t)((warp - 2) * NCH + k) * 4096u;
-          if (live) {
-            uint32_t hi[16], lo[16];
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-              const float4 v = ld_shared_v4f(sbase + (uint32_t)lane * 128u + (uint32_t)((c ^ (lane & 7)) << 4));
-              const float4 ad0 = *reinterpret_cast<const float4*>(s_tbl + sp_row * BN + c0 + 4 * c);
-              const float4 ad1 = *reinterpret_cast<const float4*>(s_tbl + sp_row * BN + c0 + 4 * c + 2);
-              float y0 = fmaf(v.x, ad0.x, ad0.y), y1 = fmaf(v.y, ad0.z, ad0.w), y2 = fmaf(v.z, ad1.x, ad1.y), y3 = fmaf(v.w, ad1.z, ad1.w);
-              if (P.fa.silu) { y0 = silu_tc(y0); y1 = silu_tc(y1); y2 = silu_tc(y2); y3 = silu_tc(y3); }
-              tc_split2(y0, y1, hi[2 * c], lo[2 * c]); tc_split2(y2, y3, hi[2 * c + 1], lo[2 * c + 1]);
-            }
-            const size_t o = m * P.Cout + n0 + c0;
-            uint4* dh = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(P.fa.hi) + o);
-            uint4* dl = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(P.fa.lo) + o);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              dh[c] = make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
-              dl[c] = make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
-            }
-          }
-        }
       }
       if (ts && lane == 0) tma_store_wait_read();     // the staging tiles must outlive the bulk stores' reads
     }
@@ -1343,10 +1200,6 @@ cudaError_t launch_conv_tc(const TcConvParams& P, cudaStream_t s) {
   const int ks = P.ksplit > 1 ? P.ksplit : 1;
   dim3 grid(tiles, P.Cout / BN, ks);
   if (ks > 1 && !P.sync) return cudaErrorInvalidValue;       // in-kernel waits need the co-residency guarantee
-  if (P.fa.hi) {                                              // local fused apply: whole samples per tile, whole groups per CTA
-    const int cpg = P.Cout / 32;
-    if (P.geo.L > TC_BM || !P.csum || P.qkv_heads || P.out_cvalid || cpg % 4 || BN % cpg || BN / cpg > TC_EPI_MAXG) return cudaErrorInvalidValue;
-  }
   if (ks > 1 && (!P.partial || P.qkv_heads)) return cudaErrorInvalidValue;
   cudaError_t e = cudaSuccess;
   const int epi = ks > 1 ? 0 : (P.qkv_heads ? 2 : (P.out_cvalid ? 4 : ((P.resid && P.resid_mode != RS_NONE) ? 3 : 1)));

@@ -122,10 +122,7 @@ struct Weight {
 };
 
 struct Tensor {
-  float* p = nullptr; int C = 0; int level = 0; double* csum = nullptr; /* channel-sum slots (csum_at), or null */
-  // set when a tensor-core conv at a small level (one tile = whole samples) produced this tensor: that kernel can also write the
-  // first simple consumer's normalised operand (FusedApply, no inter-CTA synchronisation)
-  std::shared_ptr<mtv::TcConvParams> prod;
+  float* p = nullptr; int C = 0; int level = 0; double* csum = nullptr; /* [B][3][C][2] per-channel sums, or null */
 };
 
 struct RunCtx {
@@ -176,7 +173,6 @@ struct MtvHandle_t {
   // bit 17 fused GroupNorm + qkv into the attention kernel as a cluster front end: all measured slower on B200 and removed —
   // profiles/r01_s2_chain_experiment.md, r01_s2_direct_experiment.md, r02_fused_apply_experiment.md,
   // r02_fused_attention_experiment.md.)
-  // 14 consumer GroupNorm + apply fused into the producer at the small levels (complete statistics on chip, no inter-CTA sync),
   // 18 stem conv on the tensor cores (input channels padded 16 -> 64; its channel sums replace two k_gn_stats launches)
   int tc_mask = 0x5cfff;
   cudaStream_t cap_stream = nullptr;
@@ -520,26 +516,6 @@ struct Builder {
     const int C = S.C0 + S.C1;
     const size_t bytes = (size_t)B * g.L * C * 2;
     SplitBuf out; out.hi = palloc(bytes); out.lo = palloc(bytes);
-    // a simple consumer (one source, same geometry, statistics from the producer's sums) of a small-level tensor-core conv: the
-    // producer normalises its own output on chip and writes this operand itself (kernels_tc.cu: tc_build_fa_table_local) — no
-    // apply launch.  The operand is written by an EARLIER op than the one being built, so it must not come from the pool
-    // (a pooled buffer may still be in use between the two).
-    if (norm_id >= 0 && !raw_out && S.C1 == 0 && S.resample == RS_NONE && ((h->tc_mask >> 14) & 1)) {
-      const NormSpec& n = norms[norm_id];
-      TcConvParams* pr = n.x0.prod.get();
-      if (pr && !n.has_x1 && n.x0.p == S.src0 && n.x0.C == C && pr->out == S.src0 && !pr->fa.hi && fuse_gn()) {
-        prel(out.hi); prel(out.lo);
-        out.hi = dalloc(bytes); out.lo = dalloc(bytes);
-        FusedApply& F = pr->fa;
-        F.gamma = n.gamma; F.beta = n.beta; F.joint = n.joint ? 1 : 0; F.silu = S.silu; F.hi = out.hi; F.lo = out.lo;
-        if (n.film_off >= 0) { F.film = film_buf + n.film_off; F.film_stride = h->arch.J; }
-        if (consumer_w && ((h->tc_mask >> 10) & 1)) {    // the apply kernel that would have prefetched the consumer's weights is gone
-          auto it = h->tc_w.find(consumer_w);
-          if (it != h->tc_w.end()) { pr->pf0 = it->second.first; pr->pf1 = it->second.second; pr->pf_bytes = (unsigned long long)S.taps * C * consumer_cout * 2; }
-        }
-        return out;
-      }
-    }
     ApplyParams A{};
     A.src0 = S.src0; A.src1 = S.src1; A.C0 = S.C0; A.C1 = S.C1;
     A.silu = S.silu; A.resample = S.resample; A.B = B; A.geo = g; A.hi = out.hi; A.lo = out.lo;
@@ -701,16 +677,8 @@ struct Builder {
     auto tp = std::make_shared<TcConvParams>(T);
     op.fn = [tp](cudaStream_t s) { return launch_conv_tc(*tp, s); };
     op.tc = tp;
-    {   // small level (a tile holds whole samples) and whole GroupNorm groups per CTA: the first simple consumer's apply can be fused
-      const int cpg = P.Cout / 32;
-      if (out_t && P.geo.L <= 128 && !o.qkv && !o.chmajor_valid && T.csum && cpg % 4 == 0 && bn % cpg == 0 && bn / cpg <= 32 &&
-          ((h->tc_mask >> 14) & 1))
-        out_t->prod = tp;
-    }
     pl->ops.push_back(op);
-    // operands produced by this op's own apply launches are dead now; a fused operand (written by the producer) is not pooled
-    if (pool_size.count(own0.hi)) { prel(own0.hi); prel(own0.lo); }
-    if (pool_size.count(own1.hi)) { prel(own1.hi); prel(own1.lo); }
+    prel(own0.hi); prel(own0.lo); prel(own1.hi); prel(own1.lo);
   }
   float* shared_partial = nullptr;
 
