@@ -316,6 +316,63 @@ def eager_autoencoder_times(dev):
         return {"error": repr(e)[:200]}
 
 
+def chunk_io_times(dev, hbm_peak_gbs):
+    """the per-chunk pixel work of MToV/sample.py + tools/dataloader_sample.py as device kernels
+    (moditalker_b200.chunkio), at the shipped pipeline's sizes: 16 frames, 634 x 634 sources -> 256 x 256, 478 landmarks per frame.
+    Device time per call (CUDA events on the current stream, inputs resident), algorithmic bytes / time against the HBM peak,
+    and the numpy port of the reference sequence (oracle/chunkio_oracle.py) on one host core beside it."""
+    import numpy as np
+    from moditalker_b200 import chunkio
+    try:
+        from oracle import chunkio_oracle as O
+    except Exception:
+        O = None
+    rng = np.random.default_rng(0)
+    T, H, W, R, N = 16, 634, 634, 256, 478
+    frames = rng.integers(0, 256, size=(T, H, W, 3), dtype=np.uint8)
+    rows = [int(r) for r in rng.integers(H // 3, H, size=T)]
+    lm = rng.uniform(-1, 1, size=(T, N, 3)).astype(np.float32)
+    dec = rng.uniform(-1.1, 1.1, size=(T, 3, R, R)).astype(np.float32)
+    d_frames, d_lm, d_dec = (torch.from_numpy(a).to(dev) for a in (frames, lm, dec))
+    ops = {
+        # name: (callable, algorithmic bytes, cpu port)
+        "prep_frames_x3": (lambda: [chunkio.prep_frames(d_frames, None, R), chunkio.prep_frames(d_frames, None, R), chunkio.prep_frames(d_frames, rows, R)],
+                           3 * (T * min(H, W) ** 2 * 3 + 3 * T * R * R * 4),
+                           (lambda: [O.prep_frames(frames, None, R), O.prep_frames(frames, None, R), O.prep_frames(frames, rows, R)]) if O else None),
+        "rasterize_landmarks": (lambda: chunkio.rasterize_landmarks(d_lm, H), 3 * T * 256 * 256 * 4 + lm.nbytes,
+                                (lambda: O.rasterize_landmarks(lm, H)) if O else None),
+        "frames_out": (lambda: chunkio.frames_out(d_dec, 1, 16), dec.nbytes + T * R * R * 3 + R * R * 3 + 3 * 16 * R * R * 4,
+                       (lambda: O.frames_out(dec, 1, 16)) if O else None),
+    }
+    res = {}
+    try:
+        for name, (fn, nbytes, cpu) in ops.items():
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 20
+            e0.record()
+            for _ in range(reps):
+                fn()
+            e1.record()
+            torch.cuda.synchronize(dev)
+            us = e0.elapsed_time(e1) * 1e3 / reps
+            ent = {"gpu_us": round(us, 2), "algorithmic_bytes": int(nbytes), "gb_per_s": round(nbytes / us / 1e3, 1),
+                   "hbm_frac": round(nbytes / us / 1e3 / hbm_peak_gbs, 4)}
+            if cpu is not None:
+                t0 = time.perf_counter()
+                cpu()
+                ent["cpu_port_ms"] = round((time.perf_counter() - t0) * 1e3, 1)
+            res[name] = ent
+        res["what"] = ("one 16-frame chunk: x / x_ref / masked_x from 634x634 uint8 frames (crop, bilinear to 256, mask, normalise), the "
+                       "key-point clip from 478 landmarks per frame, and decoded frames -> uint8 video + last-frame PNG pixels + next reference "
+                       "clip; includes per-call torch.empty of the outputs; cpu_port = numpy restatement of the reference sequence, 1 core")
+        return res
+    except Exception as e:      # context only
+        return {"error": repr(e)[:200]}
+
+
 def _chunk_noise_fn(chunk_ids):
     """noise_fn for DDPM: every draw is a stack of per-chunk tensors seeded by (chunk id, draw index), so a chunk sees the same
     noise whatever rank / local batch it lands in (sharding must be invisible in the output)."""
@@ -538,6 +595,7 @@ def main():
         cpu = cpu_reference_steps(args.config, args.cpu_baseline_steps, B)
     eager = None
     ae = None
+    cio = None
     if not args.no_eager_baseline and world == 1:
         try:
             eager = gpu_eager_baseline(args.config, dev, sorted({B, 8} if B == 1 else {B}))
@@ -547,6 +605,7 @@ def main():
                              speedup_device=value / eb["value"], speedup_e2e=e2e_value / eb["value"])
             if args.config == "base" and B == 1:
                 ae = eager_autoencoder_times(dev)
+                cio = chunk_io_times(dev, pk["hbm_gbs"])
         except Exception as e:
             eager = {"error": repr(e)[:300]}
 
@@ -576,6 +635,7 @@ def main():
         "kernel_families_us": {k: round(v["us_per_forward"], 1) for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["us_per_forward"])},
         "gpu_eager_baseline": eager,
         "autoencoder_eager": ae,
+        "chunk_io": cio,
         "cpu_baseline": cpu,
     }
     if gather_check is not None:

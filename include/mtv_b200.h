@@ -110,6 +110,37 @@ int  mtv_ddim_step(MtvHandle h, float* img, const float* eps, const float* noise
 int  mtv_q_sample(MtvHandle h, const float* x_start, const float* noise, int64_t n,
                   float a, float b, float* out, void* stream);
 
+/* ---- chunk I/O around the loop: the per-chunk host work of MToV/sample.py as stream-ordered device
+ * kernels.  Results are bit-exact against the reference's numpy / cv2 / torch-CPU sequence (the bilinear resize reproduces
+ * ATen's CPU kernel operation for operation).  No handle: `device` is the CUDA ordinal the pointers live on.  All pointers
+ * are DEVICE pointers. ---- */
+
+/* EvalDataset._load_img_from_path + _crop_lower_half + resize_crop (tools/dataloader_sample.py:130-146, tools/data_utils.py:73-98)
+ * followed by `x / 127.5 - 1` and "b t c h w -> b c t h w" (sample.py:322-325), for ONE clip:
+ *   frames   uint8 [T, H, W, 3]   decoded RGB frames as PIL yields them
+ *   mask_row int32 [T] or NULL    when given, frame t keeps rows < mask_row[t], the rest is zeroed and the kept pixels are
+ *                                 truncated to integers as (img * mask).astype(np.uint8) does; the host passes the row
+ *                                 numpy's `mask[int(landmarks[33][1]):, :] = 0` resolves to (negative values count from H)
+ *   out      fp32  [3, T, R, R]   centre crop to min(H, W), bilinear (align_corners = False) to R x R, normalised to [-1, 1] */
+int  mtv_io_prep_frames(int32_t device, const uint8_t* frames, int32_t T, int32_t H, int32_t W, const int32_t* mask_row,
+                        int32_t R, float* out, void* stream);
+
+/* EvalDataset._change_np_img_size (tools/dataloader_sample.py:153-180) + sample.py:324: landmark clip -> key-point video.
+ *   landmarks fp32 or fp64 (is_f64) [T, N, dims]; dims == 3: normalised coordinates, pixel = int(v * WH / 2 + WH / 2) in the
+ *             array's precision; dims == 2: pixel = int(v).  Then centre = int(pixel / WH * 256.0), and the filled radius-3
+ *             disc cv2.circle draws, clipped to the 256 x 256 canvas; flip != 0 mirrors rows (cv2.flip(img, 0))
+ *   out       fp32 [3, T, 256, 256] in {-1, +1} (white discs on black, already normalised) */
+int  mtv_io_rasterize_landmarks(int32_t device, const void* landmarks, int32_t is_f64, int32_t T, int32_t N, int32_t dims, int32_t WH,
+                                int32_t flip, float* out, void* stream);
+
+/* sample.py:380-399 and 344-358: decoded frames -> what the script writes and what the next chunk reads back.
+ *   dec       fp32  [B*T, 3, H, W]       ViTAutoencoder.decode_from_sample output (clamped to [-1, 1] here)
+ *   frames_u8 uint8 [B, T, H, W, 3]      (1 + dec) * 127.5 truncated (fake.type(torch.uint8)); may be NULL
+ *   last_u8   uint8 [B, H, W, 3]         frame T-1, clip(rint(.), 0, 255): the pixels of the PNG the script saves (RGB); may be NULL
+ *   next_ref  fp32  [B, 3, Trep, H, W]   that PNG read back: (u8 / 255) * 2 - 1, repeated Trep times along time; may be NULL */
+int  mtv_io_frames_out(int32_t device, const float* dec, int32_t B, int32_t T, int32_t H, int32_t W, uint8_t* frames_u8,
+                       uint8_t* last_u8, float* next_ref, int32_t Trep, void* stream);
+
 /* Introspection used by bench.py / tests: kernels launched by one forward at batch B
  * (graph nodes included), workspace bytes, algorithmic weight bytes read per forward. */
 int  mtv_plan_info(MtvHandle h, int32_t B, int64_t* n_launches, int64_t* workspace_bytes,

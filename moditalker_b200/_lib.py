@@ -54,6 +54,11 @@ _SIGNATURES = {
     "mtv_ddim_step": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float,
                                 c_float, c_int32, c_void_p]),
     "mtv_q_sample": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_void_p, c_void_p]),
+    "mtv_io_prep_frames": (c_int32, [c_int32, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_int32, c_void_p, c_void_p]),
+    "mtv_io_rasterize_landmarks": (c_int32, [c_int32, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p,
+                                             c_void_p]),
+    "mtv_io_frames_out": (c_int32, [c_int32, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_int32,
+                                    c_void_p]),
     "mtv_plan_info": (c_int32, [c_void_p, c_int32, POINTER(c_int64), POINTER(c_int64), POINTER(c_int64)]),
     "mtv_debug_read": (c_int32, [c_void_p, c_char_p, c_void_p, c_int64, c_void_p]),
     "mtv_debug_tc_timing": (c_int32, [c_void_p, c_void_p, c_int32, POINTER(c_int32)]),

@@ -1,0 +1,108 @@
+"""Chunk I/O around the denoising loop on the GPU.
+
+Host-side mirror of what MoDiTalker's sampling script does on the CPU for every 16-frame chunk, before and after
+``DDPM.sample``:
+
+    prep_frames            EvalDataset._load_img_from_path / _crop_lower_half / resize_crop
+                           (MToV/tools/dataloader_sample.py:130-146, MToV/tools/data_utils.py:73-98) followed by
+                           ``x / 127.5 - 1`` and the "b t c h w -> b c t h w" rearrange (MToV/sample.py:322-325)
+    lower_half_start       the row ``mask[int(landmarks[33][1]):, :] = 0`` starts at (dataloader_sample.py:134-135)
+    rasterize_landmarks    EvalDataset._change_np_img_size (dataloader_sample.py:153-180) + sample.py:324
+    frames_out             sample.py:380-399 (clamp, (1 + x) * 127.5, uint8 video frames, the last frame as the PNG's pixels)
+                           and sample.py:344-358 (that PNG read back as the next chunk's reference clip)
+
+Every function takes and returns CUDA tensors, runs on the caller's current stream through ``libmtv_b200.so`` and is
+bit-exact against the reference sequence (tests/test_chunkio_gpu.py).  There is no CPU fallback: a CPU tensor raises.
+Decoding JPEG / writing PNG and GIF files stays on the host; these functions are the pixel work between the files and the
+autoencoder.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+
+CANVAS = 256   # _change_np_img_size always draws on a 256 x 256 canvas (dataloader_sample.py:164)
+
+
+def _need_cuda(t: torch.Tensor, what: str) -> None:
+    if not (isinstance(t, torch.Tensor) and t.is_cuda):
+        raise RuntimeError(f"moditalker_b200.chunkio.{what}: expects a CUDA tensor (there is no CPU fallback)")
+
+
+def _stream(dev: torch.device) -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def lower_half_start(height: int, landmarks) -> int:
+    """Row from which ``_crop_lower_half`` zeroes a frame: ``int(landmarks[33][1])`` with numpy's slice semantics
+    (a negative value counts from the bottom; anything past the frame masks nothing)."""
+    r = int(np.asarray(landmarks)[33][1].astype(int))
+    if r < 0:
+        r = max(height + r, 0)
+    return min(r, height)
+
+
+def prep_frames(frames: torch.Tensor, mask_rows: Optional[Sequence[int]] = None, resolution: int = 256) -> torch.Tensor:
+    """uint8 frames ``[T, H, W, 3]`` (RGB, as decoded) -> fp32 ``[1, 3, T, R, R]`` in [-1, 1]: what the sampling script
+    feeds ``first_stage_model.extract``.  ``mask_rows`` (one ``lower_half_start`` per frame) selects the masked stream."""
+    _need_cuda(frames, "prep_frames")
+    if frames.dtype != torch.uint8 or frames.dim() != 4 or frames.shape[-1] != 3:
+        raise ValueError("prep_frames: frames must be uint8 [T, H, W, 3]")
+    frames = frames.contiguous()
+    T, H, W, _ = frames.shape
+    dev = frames.device
+    rows = None
+    if mask_rows is not None:
+        if len(mask_rows) != T:
+            raise ValueError("prep_frames: one mask row per frame")
+        rows = torch.tensor([int(r) for r in mask_rows], dtype=torch.int32).to(dev, non_blocking=False)
+    out = torch.empty((1, 3, T, resolution, resolution), dtype=torch.float32, device=dev)
+    lib = _lib.load_library()
+    _lib.check(lib.mtv_io_prep_frames(dev.index or 0, ctypes.c_void_p(frames.data_ptr()), T, H, W,
+                                      ctypes.c_void_p(rows.data_ptr()) if rows is not None else None,
+                                      int(resolution), ctypes.c_void_p(out.data_ptr()), _stream(dev)), "mtv_io_prep_frames")
+    return out
+
+
+def rasterize_landmarks(landmarks: torch.Tensor, WH: int, flip: bool = False) -> torch.Tensor:
+    """Landmark clip ``[T, N, 3]`` (normalised) or ``[T, N, 2]`` (pixels at size ``WH``), fp32 or fp64 as stored ->
+    key-point video fp32 ``[1, 3, T, 256, 256]`` in {-1, +1}."""
+    _need_cuda(landmarks, "rasterize_landmarks")
+    if landmarks.dtype not in (torch.float32, torch.float64) or landmarks.dim() != 3 or landmarks.shape[-1] not in (2, 3):
+        raise ValueError("rasterize_landmarks: landmarks must be fp32 / fp64 [T, N, 2 or 3]")
+    landmarks = landmarks.contiguous()
+    T, N, dims = landmarks.shape
+    dev = landmarks.device
+    out = torch.empty((1, 3, T, CANVAS, CANVAS), dtype=torch.float32, device=dev)
+    lib = _lib.load_library()
+    _lib.check(lib.mtv_io_rasterize_landmarks(dev.index or 0, ctypes.c_void_p(landmarks.data_ptr()),
+                                              1 if landmarks.dtype == torch.float64 else 0, T, N, dims, int(WH), 1 if flip else 0,
+                                              ctypes.c_void_p(out.data_ptr()), _stream(dev)), "mtv_io_rasterize_landmarks")
+    return out
+
+
+def frames_out(decoded: torch.Tensor, batch_size: int, repeat: int = 16, want_frames: bool = True,
+               want_reference: bool = True) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor], Optional[torch.Tensor]]:
+    """``decode_from_sample`` output fp32 ``[(B T), 3, H, W]`` -> ``(frames_u8 [B, T, H, W, 3], last_u8 [B, H, W, 3],
+    next_ref [B, 3, repeat, H, W])``: the video frames the script writes, the pixels of the last-frame PNG, and that PNG as
+    the script reads it back for the next chunk (ready for ``extract``)."""
+    _need_cuda(decoded, "frames_out")
+    if decoded.dtype != torch.float32 or decoded.dim() != 4 or decoded.shape[1] != 3 or decoded.shape[0] % batch_size:
+        raise ValueError("frames_out: decoded must be fp32 [(B T), 3, H, W]")
+    decoded = decoded.contiguous()
+    BT, _, H, W = decoded.shape
+    B, T = int(batch_size), BT // int(batch_size)
+    dev = decoded.device
+    frames = torch.empty((B, T, H, W, 3), dtype=torch.uint8, device=dev) if want_frames else None
+    last = torch.empty((B, H, W, 3), dtype=torch.uint8, device=dev) if want_reference else None
+    ref = torch.empty((B, 3, repeat, H, W), dtype=torch.float32, device=dev) if want_reference else None
+    lib = _lib.load_library()
+    p = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
+    _lib.check(lib.mtv_io_frames_out(dev.index or 0, p(decoded), B, T, H, W, p(frames), p(last), p(ref), int(repeat), _stream(dev)),
+               "mtv_io_frames_out")
+    return frames, last, ref

@@ -1227,6 +1227,37 @@ int mtv_q_sample(MtvHandle h, const float* x_start, const float* noise, int64_t 
   });
 }
 
+int mtv_io_prep_frames(int32_t device, const uint8_t* frames, int32_t T, int32_t H, int32_t W, const int32_t* mask_row,
+                       int32_t R, float* out, void* stream) {
+  return guarded([&] {
+    if (!frames || !out) throw MtvError("null argument");
+    if (T < 1 || H < 1 || W < 1 || R < 4 || (R & 3)) throw MtvError("mtv_io_prep_frames: need T, H, W >= 1 and a resolution that is a multiple of 4");
+    DeviceGuard dg(device);
+    CK(launch_io_prep_frames(frames, T, H, W, mask_row, R, out, (cudaStream_t)stream));
+  });
+}
+
+int mtv_io_rasterize_landmarks(int32_t device, const void* landmarks, int32_t is_f64, int32_t T, int32_t N, int32_t dims, int32_t WH,
+                               int32_t flip, float* out, void* stream) {
+  return guarded([&] {
+    if (!out || (!landmarks && T * N > 0)) throw MtvError("null argument");
+    if (T < 1 || N < 0 || (dims != 2 && dims != 3) || WH < 1) throw MtvError("mtv_io_rasterize_landmarks: need T >= 1, dims 2 or 3, WH >= 1");
+    DeviceGuard dg(device);
+    CK(launch_io_rasterize(landmarks, is_f64, T, N, dims, WH, flip, out, (cudaStream_t)stream));
+  });
+}
+
+int mtv_io_frames_out(int32_t device, const float* dec, int32_t B, int32_t T, int32_t H, int32_t W, uint8_t* frames_u8, uint8_t* last_u8,
+                      float* next_ref, int32_t Trep, void* stream) {
+  return guarded([&] {
+    if (!dec) throw MtvError("null argument");
+    if (B < 1 || T < 1 || H < 1 || W < 4 || (W & 3)) throw MtvError("mtv_io_frames_out: need B, T, H >= 1 and a width that is a multiple of 4");
+    if (next_ref && Trep < 1) throw MtvError("mtv_io_frames_out: Trep must be >= 1 when next_ref is requested");
+    DeviceGuard dg(device);
+    CK(launch_io_frames_out(dec, B, T, H, W, frames_u8, last_u8, next_ref, Trep, (cudaStream_t)stream));
+  });
+}
+
 int mtv_plan_info(MtvHandle h, int32_t B, int64_t* n_launches, int64_t* workspace_bytes, int64_t* weight_bytes) {
   return guarded([&] {
     if (!h) throw MtvError("null handle");

@@ -1,0 +1,93 @@
+"""CPU tests of the chunk I/O oracle (oracle/chunkio_oracle.py) against the fixtures the REFERENCE's own functions produced
+(oracle/make_golden_chunkio.py: EvalDataset._load_img_from_path / _crop_lower_half / _change_np_img_size,
+data_utils.resize_crop, and the literal cv2 / PIL calls of MToV/sample.py:344-399), plus the host logic of
+moditalker_b200.chunkio that needs no GPU.  Everything here is bit-exact."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from moditalker_b200 import chunkio
+from oracle import chunkio_oracle as O
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+PREP = sorted(os.path.basename(p)[8:-4] for p in glob.glob(os.path.join(GOLD, "chunkio_prep_*.npz")))
+LM = sorted(os.path.basename(p)[8:-4] for p in glob.glob(os.path.join(GOLD, "chunkio_lm_*.npz")))
+
+
+def load(name):
+    return np.load(os.path.join(GOLD, f"chunkio_{name}.npz"))
+
+
+def test_fixture_inventory():
+    assert {"prep_plain", "prep_masked", "prep_identity", "prep_up", "prep_frac"} <= set(PREP)
+    assert {"lm_norm_f32", "lm_norm_f64", "lm_pixel_f64"} <= set(LM)
+
+
+def test_to_tensor_times_255_is_the_identity_on_bytes():
+    # dataloader_sample.py:144 computes ToTensor()(img) * 255 in fp32; the kernel loads the byte directly
+    k = np.arange(256, dtype=np.uint8)
+    assert np.array_equal(O.load_255(k), k.astype(np.float32))
+    assert np.array_equal((torch.from_numpy(k).float().div(255) * 255).numpy(), k.astype(np.float32))
+
+
+@pytest.mark.parametrize("name", PREP)
+def test_prep_frames_matches_reference_fixture(name):
+    d = load(name)
+    fr = d["frames"]
+    T, H = fr.shape[0], fr.shape[1]
+    rows = [O.lower_half_start(H, d["kpts"][t]) for t in range(T)] if int(d["masked"]) else None
+    out = O.prep_frames(fr, rows, int(d["R"]))
+    assert out.dtype == np.float32 and out.shape == d["out"].shape
+    assert np.array_equal(out, d["out"])
+
+
+def test_lower_half_start_follows_numpy_slicing():
+    H = 90
+    for y, want in [(49.9, 49), (-22.5, 68), (-200.0, 0), (97.5, 90), (0.0, 0), (-0.5, 0)]:
+        k = np.zeros((68, 2))
+        k[33, 1] = y
+        mask = np.ones((H, 4))
+        mask[(k[33][1]).astype(int):, :] = 0.0            # the reference's statement (dataloader_sample.py:135)
+        first_zero = int(np.argmax(mask[:, 0] == 0)) if (mask[:, 0] == 0).any() else H
+        assert O.lower_half_start(H, k) == first_zero == want
+        assert chunkio.lower_half_start(H, k) == want      # the product's host helper agrees with the oracle
+
+
+@pytest.mark.parametrize("name", LM)
+def test_rasterize_landmarks_matches_reference_fixture(name):
+    d = load(name)
+    out = O.rasterize_landmarks(d["lm"], int(d["WH"]), bool(int(d["flip"])))
+    assert out.shape == (3, d["lm"].shape[0], 256, 256)
+    assert set(np.unique(out)) <= {-1.0, 1.0}
+    assert np.array_equal(out[0], out[1]) and np.array_equal(out[0], out[2])
+    assert np.array_equal(np.packbits(out[0] > 0), d["canvas_bits"])
+
+
+def test_rasterize_empty_and_offscreen():
+    out = O.rasterize_landmarks(np.zeros((2, 0, 3), dtype=np.float32), 256)
+    assert (out == -1).all()
+    far = np.array([[[50.0, -40.0, 0.0], [-30.0, 2.0, 0.0]]], dtype=np.float64)       # normalised coordinates far outside
+    assert (O.rasterize_landmarks(far, 634) == -1).all()
+
+
+def test_frames_out_matches_reference_fixture():
+    d = load("frames_out")
+    frames, last, ref = O.frames_out(d["dec"], int(d["B"]), 16)
+    assert np.array_equal(frames, d["frames_u8"])
+    assert np.array_equal(last, d["last_u8"])
+    assert np.array_equal(ref, d["next_ref"])
+    # planted values: the clamp edges, and two exact half-way cases that round to even (127.5 -> 128, 254.5 -> 254)
+    assert last[-1, 0, :8, 0].tolist() == [0, 255, 0, 1, 2, 128, 254, 0]
+    assert frames[-1, -1, 0, :8, 0].tolist() == [0, 255, 0, 1, 2, 127, 254, 0]
+
+
+def test_product_refuses_cpu_tensors_and_bad_shapes():
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        chunkio.prep_frames(torch.zeros(2, 8, 8, 3, dtype=torch.uint8))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        chunkio.rasterize_landmarks(torch.zeros(2, 5, 3), 256)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        chunkio.frames_out(torch.zeros(4, 3, 8, 8), 2)
