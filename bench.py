@@ -365,6 +365,16 @@ def chunk_io_times(dev, hbm_peak_gbs):
                 cpu()
                 ent["cpu_port_ms"] = round((time.perf_counter() - t0) * 1e3, 1)
             res[name] = ent
+        # the torch-CPU operations the reference's loader runs for the three RGB streams (data_utils.resize_crop = centre crop +
+        # F.interpolate(bilinear), then sample.py:322-325), all host threads, and their agreement with the device result
+        import torch.nn.functional as F
+        v = torch.from_numpy(frames).permute(0, 3, 1, 2).float()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            host = (F.interpolate(v, size=R, mode="bilinear", align_corners=False) / 127.5 - 1).permute(1, 0, 2, 3).contiguous()
+        res["prep_frames_x3"]["cpu_torch_ops_ms"] = round((time.perf_counter() - t0) * 1e3, 1)
+        res["prep_frames_x3"]["cpu_threads"] = torch.get_num_threads()
+        res["prep_frames_x3"]["max_abs_diff_vs_torch_cpu"] = float((chunkio.prep_frames(d_frames, None, R)[0].cpu() - host).abs().max())
         res["what"] = ("one 16-frame chunk: x / x_ref / masked_x from 634x634 uint8 frames (crop, bilinear to 256, mask, normalise), the "
                        "key-point clip from 478 landmarks per frame, and decoded frames -> uint8 video + last-frame PNG pixels + next reference "
                        "clip; includes per-call torch.empty of the outputs; cpu_port = numpy restatement of the reference sequence, 1 core")
