@@ -375,6 +375,10 @@ def chunk_io_times(dev, hbm_peak_gbs):
         res["prep_frames_x3"]["cpu_torch_ops_ms"] = round((time.perf_counter() - t0) * 1e3, 1)
         res["prep_frames_x3"]["cpu_threads"] = torch.get_num_threads()
         res["prep_frames_x3"]["max_abs_diff_vs_torch_cpu"] = float((chunkio.prep_frames(d_frames, None, R)[0].cpu() - host).abs().max())
+        # 634 -> 256 has exactly representable weights; an odd source size exercises the rounding of the interpolation itself
+        odd = torch.from_numpy(rng.integers(0, 256, size=(4, 633, 633, 3), dtype=np.uint8))
+        host_odd = (F.interpolate(odd.permute(0, 3, 1, 2).float(), size=R, mode="bilinear", align_corners=False) / 127.5 - 1).permute(1, 0, 2, 3)
+        res["prep_frames_x3"]["max_abs_diff_vs_torch_cpu_633"] = float((chunkio.prep_frames(odd.to(dev), None, R)[0].cpu() - host_odd).abs().max())
         res["what"] = ("one 16-frame chunk: x / x_ref / masked_x from 634x634 uint8 frames (crop, bilinear to 256, mask, normalise), the "
                        "key-point clip from 478 landmarks per frame, and decoded frames -> uint8 video + last-frame PNG pixels + next reference "
                        "clip; includes per-call torch.empty of the outputs; cpu_port = numpy restatement of the reference sequence, 1 core")

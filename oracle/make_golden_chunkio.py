@@ -148,6 +148,8 @@ def main():
     make_prep(dls, du, "prep_masked", T=3, H=90, W=64, R=40, seed=12, masked=True)       # portrait, masked stream, 1.6x down
     make_prep(dls, du, "prep_identity", T=2, H=32, W=32, R=32, seed=13, masked=True)     # no resampling: bit-exact case
     make_prep(dls, du, "prep_frac", T=2, H=50, W=70, R=36, seed=15, masked=False)        # inexact scale, unmasked (non-integer pixels)
+    make_prep(dls, du, "prep_wide", T=1, H=101, W=117, R=128, seed=16, masked=True)      # output wider than 64: torch's other loop
+    make_prep(dls, du, "prep_wide_down", T=1, H=333, W=301, R=72, seed=17, masked=False)  # ... downsampling, odd sizes
     make_prep(dls, du, "prep_up", T=2, H=20, W=20, R=32, seed=14, masked=False)          # upsampling
     make_landmarks(dls, "lm_norm_f32", T=3, N=40, WH=634, dims=3, dtype=np.float32, flip=False, seed=21)
     make_landmarks(dls, "lm_norm_f64", T=2, N=40, WH=256, dims=3, dtype=np.float64, flip=True, seed=22)

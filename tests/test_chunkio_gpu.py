@@ -41,10 +41,13 @@ def test_prep_frames_matches_reference_fixture(name):
 
 
 @pytest.mark.parametrize("H,W,R,masked", [(634, 634, 256, False), (634, 634, 256, True), (256, 256, 256, True), (360, 640, 256, False),
-                                           (726, 726, 128, True)])
+                                           (726, 726, 128, True), (633, 641, 256, True), (301, 287, 256, False), (97, 97, 64, False),
+                                           (97, 97, 68, True)])
 def test_prep_frames_matches_oracle_at_pipeline_sizes(H, W, R, masked):
+    # odd source sizes make the interpolation weights inexact in fp32, so the two rounding regimes of torch's kernel (outputs up
+    # to 64 wide / wider) are really exercised; 634 / 726 / 360 -> 256 or 128 have exact weights
     rng = np.random.default_rng(H * 7 + W + R + int(masked))
-    T = 16
+    T = 16 if H * W > 100000 else 5
     fr = rng.integers(0, 256, size=(T, H, W, 3), dtype=np.uint8)
     rows = [int(r) for r in rng.integers(0, H + 1, size=T)] if masked else None
     if masked:

@@ -22,7 +22,7 @@ def load(name):
 
 
 def test_fixture_inventory():
-    assert {"prep_plain", "prep_masked", "prep_identity", "prep_up", "prep_frac"} <= set(PREP)
+    assert {"prep_plain", "prep_masked", "prep_identity", "prep_up", "prep_frac", "prep_wide", "prep_wide_down"} <= set(PREP)
     assert {"lm_norm_f32", "lm_norm_f64", "lm_pixel_f64"} <= set(LM)
 
 
@@ -42,6 +42,29 @@ def test_prep_frames_matches_reference_fixture(name):
     out = O.prep_frames(fr, rows, int(d["R"]))
     assert out.dtype == np.float32 and out.shape == d["out"].shape
     assert np.array_equal(out, d["out"])
+
+
+def test_bilinear_matches_live_torch_cpu_over_random_sizes():
+    """torch's CPU bilinear kernel rounds differently for outputs up to 64 pixels wide and for wider ones; the oracle reproduces
+    both bit for bit.  Checked here against the installed torch over random (odd, non-dyadic) sizes on either side of the switch.
+    The fixtures pin the behaviour of the build that generated them; if the installed torch no longer reproduces a fixture
+    (another build / ISA), this live comparison is skipped rather than failed."""
+    import torch.nn.functional as F
+
+    d = load("prep_wide_down")
+    fr = d["frames"]
+    S = min(fr.shape[1], fr.shape[2])
+    y0, x0 = (fr.shape[1] - S) // 2 if fr.shape[1] > fr.shape[2] else 0, (fr.shape[2] - S) // 2 if fr.shape[2] >= fr.shape[1] else 0
+    v = torch.from_numpy(fr).permute(0, 3, 1, 2).float()[:, :, y0:y0 + S, x0:x0 + S]
+    live = (F.interpolate(v, size=int(d["R"]), mode="bilinear", align_corners=False) / 127.5 - 1).permute(1, 0, 2, 3).numpy()
+    if not np.array_equal(live, d["out"]):
+        pytest.skip("installed torch rounds its CPU bilinear kernel differently from the build that generated the fixtures")
+    rng = np.random.default_rng(7)
+    for S, R in [(37, 20), (59, 60), (358, 64), (35, 65), (101, 68), (333, 128), (211, 256), (10, 236), (64, 64), (129, 4)]:
+        img = rng.integers(0, 256, size=(2, S, S, 3)).astype(np.float32)
+        ref = F.interpolate(torch.from_numpy(img).permute(0, 3, 1, 2), size=R, mode="bilinear", align_corners=False)
+        got = O.bilinear_resize(img, R)
+        assert np.array_equal(got, ref.permute(0, 2, 3, 1).numpy()), (S, R)
 
 
 def test_lower_half_start_follows_numpy_slicing():
