@@ -112,7 +112,7 @@ int  mtv_q_sample(MtvHandle h, const float* x_start, const float* noise, int64_t
 
 /* ---- chunk I/O around the loop: the per-chunk host work of MToV/sample.py as stream-ordered device
  * kernels.  Results are bit-exact against the reference's numpy / cv2 / torch-CPU sequence (the bilinear resize reproduces
- * ATen's CPU kernel operation for operation).  No handle: `device` is the CUDA ordinal the pointers live on.  All pointers
+ * torch's CPU kernel operation for operation, including its two rounding regimes: outputs up to 64 pixels wide / wider).  No handle: `device` is the CUDA ordinal the pointers live on.  All pointers
  * are DEVICE pointers. ---- */
 
 /* EvalDataset._load_img_from_path + _crop_lower_half + resize_crop (tools/dataloader_sample.py:130-146, tools/data_utils.py:73-98)
