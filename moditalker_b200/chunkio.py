@@ -13,8 +13,10 @@ Host-side mirror of what MoDiTalker's sampling script does on the CPU for every 
 
 Every function takes and returns CUDA tensors, runs on the caller's current stream through ``libmtv_b200.so`` and is
 bit-exact against the reference sequence (tests/test_chunkio_gpu.py).  There is no CPU fallback: a CPU tensor raises.
-Decoding JPEG / writing PNG and GIF files stays on the host; these functions are the pixel work between the files and the
-autoencoder.
+Decoding JPEG and encoding PNG / GIF stay on the host; these functions are the pixel work between the files and the
+autoencoder.  ``AsyncFrameWriter`` takes the encoding off the GPU loop's critical path: pinned device-to-host copies on a side
+stream and a worker thread that writes the script's GIF / numbered PNG frames / last-frame reference PNGs under the reference's
+file names (sample.py:56-106, 385-396).
 """
 from __future__ import annotations
 
@@ -106,3 +108,115 @@ def frames_out(decoded: torch.Tensor, batch_size: int, repeat: int = 16, want_fr
     _lib.check(lib.mtv_io_frames_out(dev.index or 0, p(decoded), B, T, H, W, p(frames), p(last), p(ref), int(repeat), _stream(dev)),
                "mtv_io_frames_out")
     return frames, last, ref
+
+
+class AsyncFrameWriter:
+    """Writes what the sampling script writes per chunk — the GIF (``save_image_grid``, MToV/sample.py:56-76), the numbered PNG
+    frames (``save_image_at_folder``, sample.py:79-106) and the last-frame reference PNGs (sample.py:385-396) — without stalling
+    the GPU loop: each call enqueues a device-to-host copy into pinned memory on a side stream and returns; a worker thread waits
+    for the copy and encodes with PIL.  File names, grid layout (samples side by side, ``grid_size = (k, 1)``) and encoder
+    parameters are the reference's.  Pixels are the uint8 tensors ``frames_out`` produced, so the reference's ``normalize``
+    step (``rint((img - 0) * 255 / 255)``) is the identity and is skipped.  ``close()`` (or leaving the ``with`` block) waits for
+    every file; the first encoder error is re-raised there."""
+
+    def __init__(self, max_pending: int = 8):
+        import queue
+        import threading
+
+        self._q = queue.Queue(maxsize=max_pending)
+        self._err = None
+        self._stream = None
+        self._t = threading.Thread(target=self._run, name="mtv-frame-writer", daemon=True)
+        self._t.start()
+
+    # ---- reference file layouts -------------------------------------------------------------------------------------------
+    @staticmethod
+    def grid(frames_u8: torch.Tensor, landmarks_clip: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """``[B, T, H, W, 3]`` uint8 -> ``[T, H, B * W, 3]``: the reshape / transpose of save_image_grid for ``grid_size = (B, 1)``.
+        ``landmarks_clip`` (``x_l`` of sample.py:324, fp32 ``[B, 3, T, H, W]`` in [-1, 1]) is put in front as the script does with
+        ``--including_ldmk_video`` (sample.py:403-409: ``(x * 255 + 255) / 2``, then rint by the writer)."""
+        cols = frames_u8
+        if landmarks_clip is not None:
+            lm = ((landmarks_clip.float() * 255 + 255) / 2).round().clamp(0, 255).to(torch.uint8)     # b c t h w
+            cols = torch.cat([lm.permute(0, 2, 3, 4, 1).to(frames_u8.device), frames_u8], dim=0)
+        B, T, H, W, C = cols.shape
+        return cols.permute(1, 2, 0, 3, 4).reshape(T, H, B * W, C).contiguous()
+
+    # ---- public calls (one per file group the script writes) --------------------------------------------------------------
+    def save_gif(self, frames_u8: torch.Tensor, fname: str, landmarks_clip: Optional[torch.Tensor] = None) -> None:
+        """sample.py:411-416: ``generated_{it}.gif`` is written as ``generated_gif_{it}.gif``, 100 ms per frame, looping."""
+        fname = fname.replace("generated", "generated_gif")
+        self._submit(self.grid(frames_u8, landmarks_clip), ("gif", fname))
+
+    def save_frames(self, start_iter: int, frames_u8: torch.Tensor, folder: str, landmarks_clip: Optional[torch.Tensor] = None) -> None:
+        """sample.py:418-424: one PNG per frame, named ``str(start_iter + i).zfill(4) + ".png"``."""
+        self._submit(self.grid(frames_u8, landmarks_clip), ("frames", folder, int(start_iter)))
+
+    def save_last_frames(self, last_u8: torch.Tensor, folder: str) -> None:
+        """sample.py:385-396: ``{idx}.png`` per sample in ``references/{ldmk_end}``: the next chunk's reference frames."""
+        self._submit(last_u8.contiguous(), ("last", folder))
+
+    def close(self) -> None:
+        if self._t is not None:
+            self._q.put(None)
+            self._t.join()
+            self._t = None
+        if self._err is not None:
+            err, self._err = self._err, None
+            raise err
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False
+
+    # ---- plumbing ---------------------------------------------------------------------------------------------------------
+    def _submit(self, t: torch.Tensor, job) -> None:
+        if self._t is None:
+            raise RuntimeError("AsyncFrameWriter is closed")
+        if t.dtype != torch.uint8:
+            raise ValueError("AsyncFrameWriter: expects the uint8 tensors frames_out returns")
+        if t.is_cuda:
+            if self._stream is None:
+                self._stream = torch.cuda.Stream(device=t.device)
+            host = torch.empty(t.shape, dtype=torch.uint8, pin_memory=True)
+            self._stream.wait_stream(torch.cuda.current_stream(t.device))
+            with torch.cuda.stream(self._stream):
+                host.copy_(t, non_blocking=True)
+                t.record_stream(self._stream)
+                ev = torch.cuda.Event()
+                ev.record(self._stream)
+        else:
+            host, ev = t.clone(), None
+        self._q.put((host, ev, job))
+
+    def _run(self) -> None:
+        import os
+
+        import PIL.Image
+
+        while True:
+            item = self._q.get()
+            if item is None:
+                return
+            host, ev, job = item
+            try:
+                if ev is not None:
+                    ev.synchronize()
+                a = host.numpy()
+                if job[0] == "gif":
+                    imgs = [PIL.Image.fromarray(a[i], "RGB") for i in range(len(a))]
+                    imgs[0].save(job[1], quality=95, save_all=True, append_images=imgs[1:], duration=100, loop=0)
+                elif job[0] == "frames":
+                    os.makedirs(job[1], exist_ok=True)
+                    for i in range(len(a)):
+                        PIL.Image.fromarray(a[i], "RGB").save(os.path.join(job[1], f"{job[2] + i}".zfill(4) + ".png"))
+                else:
+                    os.makedirs(job[1], exist_ok=True)
+                    for i in range(len(a)):
+                        PIL.Image.fromarray(a[i], "RGB").save(os.path.join(job[1], f"{i}.png"))
+            except Exception as e:      # surfaced by close()
+                if self._err is None:
+                    self._err = e

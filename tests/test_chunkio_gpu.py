@@ -134,6 +134,33 @@ def test_results_do_not_depend_on_the_stream_or_on_repeats():
     assert torch.equal(a, b) and torch.equal(a, chunkio.prep_frames(fr, None, 256))
 
 
+def test_async_writer_from_device_tensors(tmp_path):
+    """frames_out -> AsyncFrameWriter: pinned copies on a side stream, files written by the worker thread hold exactly the
+    device pixels (checked after close(), while the producing stream has long moved on)."""
+    import PIL.Image
+
+    rng = np.random.default_rng(9)
+    B, T, H, W = 2, 16, 64, 64
+    with chunkio.AsyncFrameWriter() as w:
+        keep = []
+        for it in range(3):
+            dec = dev(rng.uniform(-1.1, 1.1, size=(B * T, 3, H, W)).astype(np.float32))
+            frames, last, _ = chunkio.frames_out(dec, B, 16)
+            w.save_gif(frames, str(tmp_path / f"generated_{it}.gif"))
+            w.save_frames(16 * it, frames, str(tmp_path / "frames"))
+            w.save_last_frames(last, str(tmp_path / "references" / str(16 * (it + 1))))
+            keep.append((frames.cpu().numpy(), last.cpu().numpy()))
+            del dec, frames, last                                        # the allocator may reuse the blocks: record_stream guards the copies
+    assert len(list((tmp_path / "frames").iterdir())) == 48
+    for it, (fr, la) in enumerate(keep):
+        for t in (0, 7, 15):
+            img = np.asarray(PIL.Image.open(tmp_path / "frames" / (f"{16 * it + t}".zfill(4) + ".png")))
+            assert np.array_equal(img, np.concatenate([fr[0, t], fr[1, t]], axis=1))
+        for i in range(B):
+            assert np.array_equal(np.asarray(PIL.Image.open(tmp_path / "references" / str(16 * (it + 1)) / f"{i}.png")), la[i])
+        assert PIL.Image.open(tmp_path / f"generated_gif_{it}.gif").n_frames == T
+
+
 def test_c_abi_argument_errors():
     lib = _lib.load_library()
     buf = torch.zeros(1 << 16, dtype=torch.uint8, device=DEV)

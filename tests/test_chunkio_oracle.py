@@ -114,3 +114,53 @@ def test_product_refuses_cpu_tensors_and_bad_shapes():
         chunkio.rasterize_landmarks(torch.zeros(2, 5, 3), 256)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         chunkio.frames_out(torch.zeros(4, 3, 8, 8), 2)
+
+
+def _reference_grid(img_nctHW, grid_size):
+    """The reshape / transpose of save_image_grid and save_image_at_folder (MToV/sample.py:63-67, 86-90), restated."""
+    gw, gh = grid_size
+    _N, C, T, H, W = img_nctHW.shape
+    img = img_nctHW.reshape(gh, gw, C, T, H, W).transpose(3, 0, 4, 1, 5, 2)
+    return img.reshape(T, gh * H, gw * W, C)
+
+
+def test_async_writer_files_match_the_reference_layout(tmp_path):
+    import PIL.Image
+
+    rng = np.random.default_rng(3)
+    k, T, H, W = 3, 5, 8, 12
+    frames = torch.from_numpy(rng.integers(0, 256, size=(k, T, H, W, 3), dtype=np.uint8))            # frames_out layout: b t h w c
+    x_l = torch.from_numpy(rng.choice([-1.0, 1.0], size=(k, 3, T, H, W)).astype(np.float32))          # sample.py:324
+    fakes = frames.permute(0, 4, 1, 2, 3).numpy()                                                      # sample.py:400: b c t h w
+    want = _reference_grid(fakes, (k, 1))
+    assert np.array_equal(chunkio.AsyncFrameWriter.grid(frames).numpy(), want)
+    # --including_ldmk_video (sample.py:403-409): the key-point clip in front, grid one column wider, then the writer's rint
+    both = np.concatenate([((x_l.numpy() * 255 + 255) / 2), fakes.astype(np.float32)])
+    want_lm = np.rint(_reference_grid(both, (2 * k, 1))).clip(0, 255).astype(np.uint8)
+    assert np.array_equal(chunkio.AsyncFrameWriter.grid(frames, x_l).numpy(), want_lm)
+
+    last = frames[:, -1].contiguous()
+    with chunkio.AsyncFrameWriter() as w:
+        w.save_gif(frames, str(tmp_path / "gif" / "generated_7.gif").replace("/gif/", "/"))
+        w.save_frames(32, frames, str(tmp_path / "frames"))
+        w.save_last_frames(last, str(tmp_path / "references" / "48"))
+    assert sorted(p.name for p in (tmp_path / "frames").iterdir()) == [f"{32 + i}".zfill(4) + ".png" for i in range(T)]
+    for i in range(T):
+        assert np.array_equal(np.asarray(PIL.Image.open(tmp_path / "frames" / (f"{32 + i}".zfill(4) + ".png"))), want[i])
+    for i in range(k):
+        assert np.array_equal(np.asarray(PIL.Image.open(tmp_path / "references" / "48" / f"{i}.png")), last[i].numpy())
+    gif = PIL.Image.open(tmp_path / "generated_gif_7.gif")                                             # sample.py:75: "generated" -> "generated_gif"
+    assert gif.n_frames == T and gif.info["duration"] == 100 and gif.info["loop"] == 0 and gif.size == (k * W, H)
+
+
+def test_async_writer_reports_errors_and_refuses_floats(tmp_path):
+    w = chunkio.AsyncFrameWriter()
+    with pytest.raises(ValueError):
+        w.save_last_frames(torch.zeros(1, 4, 4, 3), str(tmp_path))
+    blocker = tmp_path / "not_a_dir"
+    blocker.write_text("x")
+    w.save_last_frames(torch.zeros(1, 4, 4, 3, dtype=torch.uint8), str(blocker))      # makedirs fails in the worker
+    with pytest.raises(Exception):
+        w.close()
+    with pytest.raises(RuntimeError, match="closed"):
+        w.save_last_frames(torch.zeros(1, 4, 4, 3, dtype=torch.uint8), str(tmp_path))
