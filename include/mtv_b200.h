@@ -125,6 +125,16 @@ int  mtv_q_sample(MtvHandle h, const float* x_start, const float* noise, int64_t
 int  mtv_io_prep_frames(int32_t device, const uint8_t* frames, int32_t T, int32_t H, int32_t W, const int32_t* mask_row,
                         int32_t R, float* out, void* stream);
 
+/* Same, with flags.  MTV_IO_LOADER_WORKER: reproduce the resize as torch computes it inside a DataLoader WORKER process, which
+ * is how the shipped script runs it (get_loaders: num_workers = 4, tools/dataloader_sample.py:288-294).  A worker has one torch
+ * thread, and with one thread torch resizes 3-channel images with its "vectorized" CPU kernel at every output size; in a
+ * multi-threaded process (what mtv_io_prep_frames reproduces) it does so only while out_h + out_w <= 128 and uses its generic
+ * kernel above.  The two kernels differ in rounding (at most one ulp of the 0..255 value; identical whenever the weights are
+ * exactly representable, e.g. even source sizes at R = 256). */
+#define MTV_IO_LOADER_WORKER 1
+int  mtv_io_prep_frames_ex(int32_t device, const uint8_t* frames, int32_t T, int32_t H, int32_t W, const int32_t* mask_row,
+                           int32_t R, int32_t flags, float* out, void* stream);
+
 /* EvalDataset._change_np_img_size (tools/dataloader_sample.py:153-180) + sample.py:324: landmark clip -> key-point video.
  *   landmarks fp32 or fp64 (is_f64) [T, N, dims]; dims == 3: normalised coordinates, pixel = int(v * WH / 2 + WH / 2) in the
  *             array's precision; dims == 2: pixel = int(v).  Then centre = int(pixel / WH * 256.0), and the filled radius-3

@@ -55,6 +55,7 @@ _SIGNATURES = {
                                 c_float, c_int32, c_void_p]),
     "mtv_q_sample": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_void_p, c_void_p]),
     "mtv_io_prep_frames": (c_int32, [c_int32, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_int32, c_void_p, c_void_p]),
+    "mtv_io_prep_frames_ex": (c_int32, [c_int32, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
     "mtv_io_rasterize_landmarks": (c_int32, [c_int32, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p,
                                              c_void_p]),
     "mtv_io_frames_out": (c_int32, [c_int32, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_int32,

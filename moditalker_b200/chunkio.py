@@ -29,6 +29,7 @@ import torch
 from . import _lib
 
 CANVAS = 256   # _change_np_img_size always draws on a 256 x 256 canvas (dataloader_sample.py:164)
+MTV_IO_LOADER_WORKER = 1   # include/mtv_b200.h
 
 
 def _need_cuda(t: torch.Tensor, what: str) -> None:
@@ -49,9 +50,15 @@ def lower_half_start(height: int, landmarks) -> int:
     return min(r, height)
 
 
-def prep_frames(frames: torch.Tensor, mask_rows: Optional[Sequence[int]] = None, resolution: int = 256) -> torch.Tensor:
+def prep_frames(frames: torch.Tensor, mask_rows: Optional[Sequence[int]] = None, resolution: int = 256,
+                loader_worker: bool = False) -> torch.Tensor:
     """uint8 frames ``[T, H, W, 3]`` (RGB, as decoded) -> fp32 ``[1, 3, T, R, R]`` in [-1, 1]: what the sampling script
-    feeds ``first_stage_model.extract``.  ``mask_rows`` (one ``lower_half_start`` per frame) selects the masked stream."""
+    feeds ``first_stage_model.extract``.  ``mask_rows`` (one ``lower_half_start`` per frame) selects the masked stream.
+
+    ``loader_worker=True`` reproduces the resize as torch computes it inside a DataLoader worker process (one torch thread: its
+    "vectorized" bilinear kernel at every size), which is how the shipped script runs the loader (num_workers = 4); the default
+    reproduces a direct call in a multi-threaded process.  The two differ by at most one ulp of the 0..255 value and not at all
+    when the interpolation weights are exactly representable (e.g. even source sizes at 256)."""
     _need_cuda(frames, "prep_frames")
     if frames.dtype != torch.uint8 or frames.dim() != 4 or frames.shape[-1] != 3:
         raise ValueError("prep_frames: frames must be uint8 [T, H, W, 3]")
@@ -65,9 +72,13 @@ def prep_frames(frames: torch.Tensor, mask_rows: Optional[Sequence[int]] = None,
         rows = torch.tensor([int(r) for r in mask_rows], dtype=torch.int32).to(dev, non_blocking=False)
     out = torch.empty((1, 3, T, resolution, resolution), dtype=torch.float32, device=dev)
     lib = _lib.load_library()
-    _lib.check(lib.mtv_io_prep_frames(dev.index or 0, ctypes.c_void_p(frames.data_ptr()), T, H, W,
-                                      ctypes.c_void_p(rows.data_ptr()) if rows is not None else None,
-                                      int(resolution), ctypes.c_void_p(out.data_ptr()), _stream(dev)), "mtv_io_prep_frames")
+    rows_p = ctypes.c_void_p(rows.data_ptr()) if rows is not None else None
+    if loader_worker:
+        _lib.check(lib.mtv_io_prep_frames_ex(dev.index or 0, ctypes.c_void_p(frames.data_ptr()), T, H, W, rows_p, int(resolution),
+                                             MTV_IO_LOADER_WORKER, ctypes.c_void_p(out.data_ptr()), _stream(dev)), "mtv_io_prep_frames_ex")
+    else:
+        _lib.check(lib.mtv_io_prep_frames(dev.index or 0, ctypes.c_void_p(frames.data_ptr()), T, H, W, rows_p,
+                                          int(resolution), ctypes.c_void_p(out.data_ptr()), _stream(dev)), "mtv_io_prep_frames")
     return out
 
 

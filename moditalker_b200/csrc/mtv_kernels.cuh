@@ -134,7 +134,8 @@ cudaError_t launch_ddim_step(float* img, const float* eps, const float* noise, i
 cudaError_t launch_q_sample(const float* x0, const float* noise, int64_t n, float a, float b, float* out, cudaStream_t s);
 
 // chunk I/O around the loop (kernels_chunkio.cu)
-cudaError_t launch_io_prep_frames(const uint8_t* frames, int T, int H, int W, const int32_t* mask_row, int R, float* out, cudaStream_t s);
+cudaError_t launch_io_prep_frames(const uint8_t* frames, int T, int H, int W, const int32_t* mask_row, int R, float* out, cudaStream_t s,
+                                  bool vectorized_always = false);
 cudaError_t launch_io_rasterize(const void* lm, int lm_is_f64, int T, int N, int dims, int WH, int flip, float* out, cudaStream_t s);
 cudaError_t launch_io_frames_out(const float* dec, int B, int T, int H, int W, uint8_t* frames_u8, uint8_t* last_u8, float* next_ref, int Trep,
                                  cudaStream_t s);

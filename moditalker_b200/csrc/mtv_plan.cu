@@ -1237,6 +1237,17 @@ int mtv_io_prep_frames(int32_t device, const uint8_t* frames, int32_t T, int32_t
   });
 }
 
+int mtv_io_prep_frames_ex(int32_t device, const uint8_t* frames, int32_t T, int32_t H, int32_t W, const int32_t* mask_row,
+                          int32_t R, int32_t flags, float* out, void* stream) {
+  return guarded([&] {
+    if (!frames || !out) throw MtvError("null argument");
+    if (T < 1 || H < 1 || W < 1 || R < 4 || (R & 3)) throw MtvError("mtv_io_prep_frames_ex: need T, H, W >= 1 and a resolution that is a multiple of 4");
+    if (flags & ~1) throw MtvError("mtv_io_prep_frames_ex: unknown flag bits");
+    DeviceGuard dg(device);
+    CK(launch_io_prep_frames(frames, T, H, W, mask_row, R, out, (cudaStream_t)stream, (flags & 1) != 0));
+  });
+}
+
 int mtv_io_rasterize_landmarks(int32_t device, const void* landmarks, int32_t is_f64, int32_t T, int32_t N, int32_t dims, int32_t WH,
                                int32_t flip, float* out, void* stream) {
   return guarded([&] {

@@ -45,24 +45,26 @@ def sample_chunks(first_stage_model, first_stage_model_ldmk, diffusion_model, ch
                   batch_size: int = 1, use_last_as_reference: bool = True, x_noisy_start: bool = True,
                   refvid_noisy_start: bool = False, ratio_: float = 0.25, fix_noise: bool = True, resolution: int = 256,
                   writer: Optional[chunkio.AsyncFrameWriter] = None, out_dir: Optional[str] = None,
-                  including_ldmk_video: bool = False) -> Iterator[ChunkResult]:
+                  including_ldmk_video: bool = False, loader_worker: bool = False) -> Iterator[ChunkResult]:
     """MToV/sample.py:305-428.  Keyword names are the script's command-line flags; ``batch_size`` is its ``k``.
 
     ``first_stage_model`` / ``first_stage_model_ldmk`` need ``extract`` and ``decode_from_sample`` (autoencoder_vit.py:212-275),
     ``diffusion_model`` is ``moditalker_b200.DDPM`` (or the reference's own).  With ``writer`` and ``out_dir`` the chunk's GIF,
-    numbered frames and last-frame PNGs are written as the script writes them (``gif/``, ``frames/``, ``references/<frame>/``)."""
+    numbered frames and last-frame PNGs are written as the script writes them (``gif/``, ``frames/``, ``references/<frame>/``).
+    ``loader_worker=True`` resizes as torch does inside the script's DataLoader workers (see ``chunkio.prep_frames``)."""
     dev = torch.device(device)
     k = int(batch_size)
     prev_ref = None                                                        # previous chunk's last frames, as read back
+    lw = {"loader_worker": True} if loader_worker else {}                  # default: the verified direct-call form, no extra argument
     for it, ch in enumerate(chunks):
         ldmk_srt, ldmk_end = it * 16, it * 16 + 16
         frames = ch.frames_u8.to(dev, non_blocking=True)
         T, H, W, _ = frames.shape
         # the four clips of sample.py:318-325 (x_ref: frame 0 repeated, dataloader_sample.py:192-193)
-        x = chunkio.prep_frames(frames, None, resolution)
-        x_ref = chunkio.prep_frames(ch.first_frame_u8.to(dev, non_blocking=True).unsqueeze(0).expand(T, -1, -1, -1), None, resolution)
+        x = chunkio.prep_frames(frames, None, resolution, **lw)
+        x_ref = chunkio.prep_frames(ch.first_frame_u8.to(dev, non_blocking=True).unsqueeze(0).expand(T, -1, -1, -1), None, resolution, **lw)
         rows = [chunkio.lower_half_start(H, ch.keypoints[t]) for t in range(T)]
-        masked_x = chunkio.prep_frames(frames, rows, resolution)
+        masked_x = chunkio.prep_frames(frames, rows, resolution, **lw)
         x_l = chunkio.rasterize_landmarks(ch.landmarks.to(dev, non_blocking=True), W)   # WH = vid.shape[-1] (dataloader_sample.py:215)
         if k > 1:                                                          # the script's loader batch is 1; k identities share the clips
             x, x_ref, masked_x, x_l = (t.expand(k, -1, -1, -1, -1) for t in (x, x_ref, masked_x, x_l))

@@ -50,7 +50,7 @@ def ref_modules():
     return dls, du
 
 
-def make_prep(dls, du, name, T, H, W, R, seed, masked):
+def make_prep(dls, du, name, T, H, W, R, seed, masked, worker=False):
     import PIL.Image
     from einops import rearrange
     from torchvision import transforms
@@ -75,11 +75,18 @@ def make_prep(dls, du, name, T, H, W, R, seed, masked):
         vid = np.stack([load(t) for t in range(T)], axis=0)                              # [T, 3, H, W] fp32 0..255
         if masked:
             vid = np.stack([dls.EvalDataset._crop_lower_half(stub, load(t), kpts[t]) for t in range(T)], axis=0)
+    if worker:
+        # the shipped script runs the loader in DataLoader workers (get_loaders: num_workers=4); a worker process has ONE torch
+        # thread, and with one thread torch resizes 3-channel input with its other CPU kernel
+        nthreads = torch.get_num_threads()
+        torch.set_num_threads(1)
     out = du.resize_crop(torch.from_numpy(vid).float(), resolution=R)                    # c t h w
+    if worker:
+        torch.set_num_threads(nthreads)
     x = rearrange(out, "c t h w -> t c h w")[None]                                       # DataLoader batch of 1
     x = rearrange(x / 127.5 - 1, "b t c h w -> b c t h w")[0]                            # sample.py:322-325
     np.savez_compressed(os.path.join(GOLD, f"chunkio_{name}.npz"), frames=frames, kpts=kpts, R=R, masked=int(masked),
-                        out=x.numpy().astype(np.float32))
+                        worker=int(worker), out=x.numpy().astype(np.float32))
     print(name, x.shape, float(x.min()), float(x.max()))
 
 
@@ -150,6 +157,7 @@ def main():
     make_prep(dls, du, "prep_frac", T=2, H=50, W=70, R=36, seed=15, masked=False)        # inexact scale, unmasked (non-integer pixels)
     make_prep(dls, du, "prep_wide", T=1, H=101, W=117, R=128, seed=16, masked=True)      # output wider than 64: torch's other loop
     make_prep(dls, du, "prep_wide_down", T=1, H=333, W=301, R=72, seed=17, masked=False)  # ... downsampling, odd sizes
+    make_prep(dls, du, "prep_worker", T=1, H=205, W=187, R=96, seed=18, masked=True, worker=True)   # as in a DataLoader worker
     make_prep(dls, du, "prep_up", T=2, H=20, W=20, R=32, seed=14, masked=False)          # upsampling
     make_landmarks(dls, "lm_norm_f32", T=3, N=40, WH=634, dims=3, dtype=np.float32, flip=False, seed=21)
     make_landmarks(dls, "lm_norm_f64", T=2, N=40, WH=256, dims=3, dtype=np.float64, flip=True, seed=22)

@@ -22,7 +22,7 @@ def load(name):
 
 
 def test_fixture_inventory():
-    assert {"prep_plain", "prep_masked", "prep_identity", "prep_up", "prep_frac", "prep_wide", "prep_wide_down"} <= set(PREP)
+    assert {"prep_plain", "prep_masked", "prep_identity", "prep_up", "prep_frac", "prep_wide", "prep_wide_down", "prep_worker"} <= set(PREP)
     assert {"lm_norm_f32", "lm_norm_f64", "lm_pixel_f64"} <= set(LM)
 
 
@@ -39,9 +39,11 @@ def test_prep_frames_matches_reference_fixture(name):
     fr = d["frames"]
     T, H = fr.shape[0], fr.shape[1]
     rows = [O.lower_half_start(H, d["kpts"][t]) for t in range(T)] if int(d["masked"]) else None
-    out = O.prep_frames(fr, rows, int(d["R"]))
+    out = O.prep_frames(fr, rows, int(d["R"]), loader_worker=bool(int(d["worker"])))
     assert out.dtype == np.float32 and out.shape == d["out"].shape
     assert np.array_equal(out, d["out"])
+    if name == "prep_worker":                  # the two torch kernels really differ on this case: the flag is not a no-op
+        assert not np.array_equal(O.prep_frames(fr, rows, int(d["R"]), loader_worker=False), d["out"])
 
 
 def test_bilinear_matches_live_torch_cpu_over_random_sizes():
@@ -65,6 +67,35 @@ def test_bilinear_matches_live_torch_cpu_over_random_sizes():
         ref = F.interpolate(torch.from_numpy(img).permute(0, 3, 1, 2), size=R, mode="bilinear", align_corners=False)
         got = O.bilinear_resize(img, R)
         assert np.array_equal(got, ref.permute(0, 2, 3, 1).numpy()), (S, R)
+
+
+def test_bilinear_worker_form_matches_live_torch_cpu_with_one_thread():
+    """Inside a DataLoader worker torch has one thread and resizes 3-channel input with its vectorized kernel at every size
+    (`loader_worker=True`).  Same live comparison as above under torch.set_num_threads(1); skipped if the installed torch does
+    not reproduce the worker fixture."""
+    import torch.nn.functional as F
+
+    n = torch.get_num_threads()
+    torch.set_num_threads(1)
+    try:
+        d = load("prep_worker")
+        fr = d["frames"]
+        H, W = fr.shape[1:3]
+        S = min(H, W)
+        y0, x0 = ((H - W) // 2 if H > W else 0), ((W - H) // 2 if W >= H else 0)
+        rows = np.array([O.lower_half_start(H, d["kpts"][t]) for t in range(fr.shape[0])])
+        v = np.where(np.arange(H)[None, :, None, None] < rows[:, None, None, None], fr, 0).astype(np.float32)
+        t = torch.from_numpy(v).permute(0, 3, 1, 2)[:, :, y0:y0 + S, x0:x0 + S]
+        live = (F.interpolate(t, size=int(d["R"]), mode="bilinear", align_corners=False) / 127.5 - 1).permute(1, 0, 2, 3).numpy()
+        if not np.array_equal(live, d["out"]):
+            pytest.skip("installed torch rounds its single-thread CPU bilinear kernel differently from the build that generated the fixtures")
+        rng = np.random.default_rng(8)
+        for S, R in [(37, 20), (101, 68), (333, 128), (211, 256), (10, 236)]:
+            img = rng.integers(0, 256, size=(2, S, S, 3)).astype(np.float32)
+            ref = F.interpolate(torch.from_numpy(img).permute(0, 3, 1, 2), size=R, mode="bilinear", align_corners=False)
+            assert np.array_equal(O.bilinear_resize(img, R, vectorized=True), ref.permute(0, 2, 3, 1).numpy()), (S, R)
+    finally:
+        torch.set_num_threads(n)
 
 
 def test_lower_half_start_follows_numpy_slicing():
